@@ -1,0 +1,253 @@
+/*
+ * needle_b200.h -- C ABI of the B200-native fingerprint-and-match path for
+ * aksiksi/needle.  Plain pointers and sizes only; every entry point returns an
+ * int status (NB200_OK == 0), never throws or aborts across the boundary.
+ *
+ * What each group replaces in the reference (paths relative to the needle repo):
+ *
+ *   B1 fingerprint  nb200_fp_*            the chromaprint_rust::Context calls made by
+ *                                         Analyzer::process_frames
+ *                                         (needle/src/audio/analyzer.rs:176,179,218,275,
+ *                                          286,288,289,299-301)
+ *                   nb200_fingerprint_*   the per-video loop of Analyzer::run
+ *                                         (analyzer.rs:437-445) + the subsample/timestamp
+ *                                         tail of process_frames (analyzer.rs:288-318)
+ *   B2 match        nb200_match_*         Comparator::longest_common_hash_match for every
+ *                                         pair (needle/src/audio/comparator.rs:157-250,
+ *                                          pair loop :532-578)
+ *                   nb200_search          Comparator::run_with_frame_hashes
+ *                                         (comparator.rs:524-629) without display / skip files
+ *   persistence     nb200_framehashes_*   FrameHashes bincode (.needle.dat,
+ *                                         needle/src/audio/data.rs:15-26,104-115;
+ *                                         analyzer.rs:413-417)
+ *
+ * There is no CPU fallback: every compute entry point needs a CUDA device
+ * (sm_100a) and fails with NB200_ERR_CUDA otherwise.
+ *
+ * Threading: a context owns one CUDA stream and scratch buffers; calls on the
+ * same context must not overlap, distinct contexts are independent (needle's
+ * rayon workers would each own one, or share one behind a mutex).
+ */
+#ifndef NEEDLE_B200_H
+#define NEEDLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+enum {
+    NB200_OK = 0,
+    NB200_ERR_NULL_ARGUMENT = 1,     /* NeedleError_NullArgument */
+    NB200_ERR_INVALID_ARGUMENT = 2,  /* NeedleError_InvalidArgument */
+    NB200_ERR_CUDA = 3,              /* any CUDA runtime failure / no device */
+    NB200_ERR_NO_ENDING = 4,         /* Error::FrameHashDataNoEnding (comparator.rs:271-273) */
+    NB200_ERR_DURATION_UNDERFLOW = 5,/* the reference would panic on Duration - Duration */
+    NB200_ERR_TOO_LARGE = 6,         /* an index does not fit the device layout */
+    NB200_ERR_IO = 7,                /* NeedleError_IOError */
+    NB200_ERR_FORMAT = 8,            /* NeedleError_InvalidFrameHashData / InvalidVersion */
+    NB200_ERR_STATE = 9,             /* call order violated (e.g. feed before start) */
+    NB200_ERR_COMPARATOR_MINIMUM_PATHS = 10, /* NeedleError_ComparatorMinimumPaths */
+};
+const char *nb200_status_str(int status);
+/* Last CUDA error text seen by this thread ("" if none). */
+const char *nb200_last_error(void);
+
+/* ----------------------------------------------------------------- context */
+typedef struct nb200_ctx nb200_ctx;
+/* device < 0: use the calling thread's current CUDA device. */
+int nb200_ctx_create(int device, nb200_ctx **out);
+void nb200_ctx_destroy(nb200_ctx *ctx);
+/* Run on a caller-owned cudaStream_t instead of the context's own stream
+ * (NULL restores it).  Lets a host time the kernels with its own events. */
+int nb200_ctx_set_stream(nb200_ctx *ctx, void *cuda_stream);
+int nb200_ctx_synchronize(nb200_ctx *ctx);
+/* Milliseconds of the kernels of the last *_run call, from CUDA events on the
+ * context's stream: [0] fingerprint K1 (fft+chroma), [1] K2 (classify),
+ * [2] match K3, [3] simhash K4.  Counters of launches since context creation
+ * in n_launches (may be NULL). */
+int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
+
+/* Pinned host memory (cudaHostAlloc) for PCM / hash staging. */
+int nb200_host_alloc(void **out, size_t bytes);
+int nb200_host_free(void *p);
+/* Frees any buffer this library returned through an out-pointer. */
+void nb200_free(void *p);
+
+/* ---------------------------------------------------------- shared structs */
+
+/* Comparator configuration (comparator.rs:74-82, defaults audio/mod.rs:14-45) */
+typedef struct nb200_match_params {
+    uint32_t hash_match_threshold;   /* default 10, <= 32 */
+    uint32_t include_endings;        /* 0/1 */
+    uint64_t min_opening_ns;         /* default 20 s */
+    uint64_t min_ending_ns;          /* default 20 s */
+    uint64_t time_padding_ns;        /* default 0 */
+} nb200_match_params;
+void nb200_match_params_default(nb200_match_params *p);
+
+/* One maximal diagonal run that passed the duration filter == one
+ * ComparatorHeapEntry (comparator.rs:20-35, built at :231-243):
+ * score = len, src run = ts_src[i_end-len]..ts_src[i_end], likewise dst. */
+typedef struct nb200_run {
+    uint32_t pair;        /* index into the pair list */
+    uint32_t is_ending;   /* 0: opening x opening table, 1: ending x ending */
+    uint32_t i_end;       /* src index of the last matching cell */
+    uint32_t j_end;       /* dst index of the last matching cell */
+    uint32_t len;         /* table[i_end][j_end] */
+    uint32_t src_simhash; /* simhash32(src[i_end-len ..= i_end]) (comparator.rs:149-153) */
+    uint32_t dst_simhash;
+    uint32_t reserved;
+} nb200_run;
+
+/* SearchResult (comparator.rs:65-69) with the video index kept: element v
+ * of the results array belongs to video v; present == 0 means the reference's
+ * results Vec has no element for it (find_best_match returned None). */
+typedef struct nb200_search_result {
+    uint32_t present, has_opening, has_ending, reserved;
+    uint64_t opening_start_ns, opening_end_ns;
+    uint64_t ending_start_ns, ending_end_ns;
+} nb200_search_result;
+
+/* ------------------------------------------------- B2: match, host buffers */
+
+/* A season in SoA form: video k's opening list is
+ * hashes[seg_offset[2k] .. seg_offset[2k+1]), its ending list
+ * hashes[seg_offset[2k+1] .. seg_offset[2k+2]); ts_ns likewise.
+ * (FrameHashes::opening_data / ending_data, data.rs:143-155.)
+ *
+ * pairs == NULL: all (i < j) in the reference's order (comparator.rs:534-545).
+ * Runs are returned sorted by (pair, is_ending, i_end desc, j_end desc) = the
+ * reference's heap-push order (comparator.rs:191-192); *out_runs is owned by
+ * the caller (nb200_free). */
+int nb200_match_pairs(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                      const uint64_t *seg_offset, uint32_t n_videos,
+                      const uint32_t (*pairs)[2], uint64_t n_pairs,
+                      const nb200_match_params *params, nb200_run **out_runs, uint64_t *out_n);
+
+/* Comparator::run_with_frame_hashes: match every pair on the GPU, then replay
+ * the reference's BinaryHeap pushes and find_best_match on the host.
+ * hash_duration_ns[n_videos] = FrameHashes::hash_duration per video.
+ * results[n_videos]. */
+int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                 const uint64_t *seg_offset, const uint64_t *hash_duration_ns, uint32_t n_videos,
+                 const nb200_match_params *params, nb200_search_result *results);
+
+/* Host-only tail of nb200_search for callers that gathered runs themselves
+ * (multi-GPU: every rank matches its share of the pair list, rank 0 votes).
+ * runs must be sorted as nb200_match_pairs returns them; pairs as above. */
+int nb200_vote(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
+               const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
+               uint64_t n_runs, nb200_search_result *results);
+
+/* ------------------------------------------ device-resident staged pipeline */
+
+typedef struct nb200_hashset nb200_hashset; /* a season of hashes + timestamps in HBM */
+typedef struct nb200_pcmset nb200_pcmset;   /* decoded PCM segments in HBM */
+typedef struct nb200_runset nb200_runset;   /* match output in HBM */
+
+int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                         const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out);
+/* Sizes: total = number of hashes; seg_offset_out[2*n_videos+1] (may be NULL). */
+int nb200_hashset_info(const nb200_hashset *hs, uint32_t *n_videos, uint64_t *total,
+                       uint64_t *seg_offset_out);
+int nb200_hashset_download(nb200_ctx *ctx, const nb200_hashset *hs, uint32_t *hashes_out,
+                           uint64_t *ts_ns_out);
+/* Raw device pointers of the packed (contiguous, seg_offset-indexed) arrays,
+ * for collectives run by the host framework (e.g. NCCL all-gather). */
+int nb200_hashset_device_ptrs(const nb200_hashset *hs, void **d_hashes, void **d_ts_ns);
+/* Wrap device arrays already laid out like nb200_hashset_upload's inputs
+ * (e.g. the result of an all-gather).  Copies device-to-device. */
+int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                              const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out);
+void nb200_hashset_free(nb200_hashset *hs);
+
+/* Launch the match kernels for the given pairs (NULL = all i<j); returns once
+ * the kernels are enqueued and the run count is known. */
+int nb200_match_run(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
+                    uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out);
+int nb200_runset_count(const nb200_runset *rs, uint64_t *n_runs, uint64_t *n_cells);
+/* Sorted like nb200_match_pairs' output; runs_out sized by nb200_runset_count. */
+int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *runs_out);
+void nb200_runset_free(nb200_runset *rs);
+
+/* --------------------------------------------------------- B1: fingerprint */
+
+/* Chromaprint constants needle reads back (analyzer.rs:288-289) */
+#define NB200_SAMPLE_RATE 11025
+#define NB200_DELAY_MS 2600          /* chromaprint_get_delay_ms */
+#define NB200_ITEM_DURATION_MS 123   /* chromaprint_get_item_duration_ms */
+
+/* Number of raw sub-fingerprints for n mono samples: frames - 19 */
+uint64_t nb200_num_raw_hashes(uint64_t n_mono_samples);
+
+/* H2D of n_segments PCM buffers (interleaved i16 @ 11025 Hz, channels 1|2;
+ * n_samples_total[k] counts i16 values, i.e. frames*channels, as needle passes
+ * to feed, analyzer.rs:263-275).  Pinned source buffers copy at full PCIe rate. */
+int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                        int channels, uint32_t n_segments, nb200_pcmset **out);
+void nb200_pcmset_free(nb200_pcmset *ps);
+
+/* Fingerprint every segment on the GPU and keep raw index 0, stride, 2*stride..
+ * (step_by, analyzer.rs:293-305), stamped
+ *   ts = delay + item.mul_f32(i as f32) + seek_to   (analyzer.rs:309,314-318).
+ * Segments 2k and 2k+1 become video k's opening and ending lists; pass
+ * n_segments = 2*n_videos with empty ending segments when endings are off.
+ * seek_to_ns may be NULL (all zero). */
+int nb200_fingerprint_run(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride,
+                          uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
+                          nb200_hashset **out);
+
+/* One-shot with host buffers: raw sub-fingerprints (stride 1, no timestamps)
+ * of each segment == chromaprint_get_raw_fingerprint.  out_hashes[k] is
+ * nb200_free'd by the caller. */
+int nb200_fingerprint_batch(nb200_ctx *ctx, const int16_t *const *pcm,
+                            const uint64_t *n_samples_total, int channels, uint32_t n_segments,
+                            uint32_t stride, uint32_t **out_hashes, uint64_t *out_counts);
+
+/* Chromaprint-shaped streaming shim: a type swap for chromaprint::Context in
+ * Analyzer::process_frames.  feed() accumulates (down-mixing stereo) into a
+ * pinned buffer; finish() runs the kernels. */
+typedef struct nb200_fp nb200_fp;
+int nb200_fp_new(nb200_ctx *ctx, nb200_fp **out);          /* Context::default()        :176 */
+void nb200_fp_free(nb200_fp *fp);
+int nb200_fp_sample_rate(const nb200_fp *fp);              /* Context::sample_rate()    :179 */
+int nb200_fp_start(nb200_fp *fp, int sample_rate, int channels); /* start(rate, 2)      :218 */
+int nb200_fp_feed(nb200_fp *fp, const int16_t *data, size_t n_samples_total); /* feed   :275 */
+int nb200_fp_finish(nb200_fp *fp);                         /* finish()                  :286 */
+int nb200_fp_get_delay_ms(const nb200_fp *fp, int *out);   /* get_delay()               :288 */
+int nb200_fp_get_item_duration_ms(const nb200_fp *fp, int *out); /* get_item_duration() :289 */
+/* Borrowed pointer, valid until the next start()/free() (get_fingerprint_raw :299-301). */
+int nb200_fp_get_raw(const nb200_fp *fp, const uint32_t **hashes, size_t *n);
+
+/* ------------------------------------------------ fused analyze + search */
+
+/* `needle search --analyze`: PCM segments (2 per video: opening, ending) ->
+ * fingerprints -> all-pairs match -> vote, hashes never leaving HBM.
+ * hash_duration_ns: what Analyzer was asked for (Duration::from_secs_f32(0.3)
+ * = 300000012); stride = hash_duration_ms / 123 (analyzer.rs:293-297). */
+int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                         int channels, uint32_t n_videos, const uint64_t *seek_to_ns,
+                         uint64_t hash_duration_ns, const nb200_match_params *params,
+                         nb200_search_result *results);
+
+/* ------------------------------------------------------------ persistence */
+
+/* .needle.dat (bincode 1.3, fixint little-endian) of one video.
+ * write: opening/ending as (hash, ts_ns) SoA; md5 = 32 hex chars. */
+int nb200_framehashes_write(const char *path, const uint32_t *open_hash, const uint64_t *open_ts_ns,
+                            uint64_t n_open, const uint32_t *end_hash, const uint64_t *end_ts_ns,
+                            uint64_t n_end, uint64_t hash_duration_ns, const char *md5);
+/* read: out arrays are nb200_free'd by the caller; md5_out holds >= 33 bytes. */
+int nb200_framehashes_read(const char *path, uint32_t **open_hash, uint64_t **open_ts_ns,
+                           uint64_t *n_open, uint32_t **end_hash, uint64_t **end_ts_ns,
+                           uint64_t *n_end, uint64_t *hash_duration_ns, char *md5_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEEDLE_B200_H */

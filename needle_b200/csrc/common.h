@@ -1,0 +1,163 @@
+// common.h -- internal declarations shared by the translation units of
+// libneedle_b200.so.  Not part of the C ABI (that is include/needle_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/needle_b200.h"
+
+namespace nb200 {
+
+void set_last_error(const char *what, cudaError_t e);
+void set_last_error_msg(const std::string &msg);
+
+#define NB_CUDA(expr)                                      \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) {                           \
+            ::nb200::set_last_error(#expr, _e);            \
+            return NB200_ERR_CUDA;                         \
+        }                                                  \
+    } while (0)
+
+#define NB_TRY(expr)                   \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != NB200_OK) return _s; \
+    } while (0)
+
+// Simple RAII device buffer.
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;
+        NB_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return NB200_OK;
+    }
+    // Grow-only (amortised scratch).
+    int reserve(size_t n) {
+        if (n <= bytes) return NB200_OK;
+        return alloc(n + n / 4);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    int reserve(size_t n) {
+        if (n <= bytes) return NB200_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        n += n / 4;
+        NB_CUDA(cudaHostAlloc(&p, n, cudaHostAllocDefault));
+        bytes = n;
+        return NB200_OK;
+    }
+    ~PinnedBuf() {
+        if (p) cudaFreeHost(p);
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace nb200
+
+// ---------------------------------------------------------------- objects
+
+struct nb200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;     // the one in use (own or caller's)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
+    bool ev_valid[4] = {false, false, false, false};
+    uint64_t n_launches = 0;
+    // scratch reused across calls
+    nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_runs_sorted;
+    nb200::PinnedBuf h_stage, h_small;
+};
+
+// Device layout of a season: every segment starts at a multiple of 4 elements
+// (16 B, the granularity of cp.async.bulk) in d_hashes / d_ts.
+struct nb200_hashset {
+    uint32_t n_videos = 0;
+    std::vector<uint64_t> seg_offset;   // caller's packed offsets [2N+1]
+    std::vector<uint32_t> dev_offset;   // aligned device offsets [2N]
+    std::vector<uint32_t> seg_len;      // [2N]
+    std::vector<uint32_t> seg_lmin_open, seg_lmin_end;  // filled lazily per params
+    uint64_t total = 0;                 // packed element count
+    uint64_t dev_total = 0;             // aligned element count
+    nb200::DevBuf d_hashes, d_ts;
+    // host mirrors of the timestamps (needed for the run-length lower bound);
+    // empty when the set was produced on the device and not yet mirrored
+    std::vector<uint64_t> h_ts;
+    bool ts_on_host = false;
+    // timestamps follow the analyzer formula with these parameters (device-made sets)
+    bool ts_formula = false;
+    uint64_t delay_ns = 0, item_ns = 0;
+    uint32_t stride = 1;
+    std::vector<uint64_t> seek_to_ns;   // [2N]
+};
+
+struct nb200_pcmset {
+    uint32_t n_segments = 0;
+    int channels = 1;
+    std::vector<uint64_t> n_frames_pcm;   // mono sample count per segment
+    std::vector<uint64_t> dev_offset;     // element (i16) offset of each segment, 8-aligned
+    nb200::DevBuf d_pcm;
+};
+
+struct nb200_runset {
+    uint64_t n_runs = 0;
+    uint64_t n_cells = 0;
+    std::vector<uint32_t> problem_pair;     // per problem: pair index
+    std::vector<uint8_t> problem_is_ending;
+    nb200::DevBuf d_runs;                   // DeviceRun[n_runs], unsorted, simhashes filled
+};
+
+namespace nb200 {
+
+// match.cu ---------------------------------------------------------------
+struct DeviceRun {
+    uint32_t problem;
+    uint32_t i_end, j_end, len;
+    uint32_t src_simhash, dst_simhash;
+};
+
+int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
+                   uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out);
+
+// vote.cpp ---------------------------------------------------------------
+void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order
+int vote_impl(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
+              const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+              uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
+              uint64_t n_runs, nb200_search_result *results);
+// Smallest run length that can satisfy ts[i] - ts[i-len] >= min_ns anywhere in
+// the list (1 if the list is not monotone, so that every run is examined).
+uint32_t min_qualifying_len(const uint64_t *ts, size_t n, uint64_t min_ns);
+
+// fingerprint.cu -----------------------------------------------------------
+int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
+                         uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out);
+uint64_t num_frames(uint64_t n_mono);
+
+}  // namespace nb200

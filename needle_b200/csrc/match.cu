@@ -1,0 +1,563 @@
+// match.cu -- K3/K4: the Comparator's all-pairs sliding match on sm_100a.
+//
+// Replaces Comparator::longest_common_hash_match
+// (needle/src/audio/comparator.rs:157-250) for every pair of the pair loop
+// (comparator.rs:532-578).  The reference fills an (n+1)x(m+1) usize table
+// (table[i][j] = table[i-1][j-1]+1 iff popcount(src[i]^dst[j]) <= T, rows and
+// columns 0 forced to 0, :175-187) and scans it backwards for run ends
+// (:191-200).  A run lives on one diagonal d = i - j, so no table is needed:
+// this kernel walks diagonals, packs the match predicate of 32 consecutive
+// cells of a diagonal into one word, and extracts maximal runs from the words.
+//
+// Work decomposition (all integer, CUDA cores; 1 LOP3 + 1 POPC per cell):
+//   problem   = one table (pair x {opening, ending})
+//   row chunk = MATCH_R consecutive src rows
+//   warp tile = one row chunk x 32*C adjacent diagonals; lane l owns the C
+//               diagonals dband + l*C .. dband + l*C + C-1
+// Persistent warps pull warp tiles from a global counter.  Per 32-row step a
+// lane holds the 32 src hashes of the step (warp-uniform) and a sliding window
+// of 32+C-1 dst hashes in registers (both staged through shared memory), so a
+// cell costs no memory instruction.
+//
+// Runs that cross a row-chunk boundary are owned by the tile in which they
+// START: a tile ignores a run that is already active in the row above its
+// first row, and keeps walking past its last row while a run it owns is still
+// active.  That makes tiles independent and the result exact.
+//
+// The duration filter of :212-223 is evaluated exactly, on the u64 ns
+// timestamps, for every run that reaches `lcand` cells -- a per-problem lower
+// bound on the length of any qualifying run computed on the host from the same
+// timestamps (vote.cpp: min_qualifying_len).  Runs shorter than that cannot
+// pass the filter, so skipping them changes nothing.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+
+namespace nb200 {
+
+constexpr int MATCH_R = 256;          // rows per chunk
+constexpr int MATCH_C = 8;            // diagonals per lane
+constexpr int MATCH_DW = 32 * MATCH_C;  // diagonals per warp tile
+constexpr int MATCH_WARPS = 4;        // warps per CTA (independent workers)
+constexpr int SRC_TILE = MATCH_R + 8;             // rows r0-4 .. r0+R+3
+constexpr int DST_TILE = MATCH_R + MATCH_DW + 8;  // cols tile_j0 .. tile_j0+R+263
+constexpr int LUT_SHIFT = 7;
+constexpr int FOREIGN = -(1 << 30);   // carry marker: run started in an earlier chunk
+
+struct MatchProblem {
+    uint32_t src_off, n;    // element offset into d_hashes / d_ts, length
+    uint32_t dst_off, m;
+    uint64_t min_ns;        // min_opening_duration or min_ending_duration
+    uint32_t lcand;         // >= 1
+    uint32_t n_bands;       // warp tiles per row chunk
+    uint32_t tile_begin;    // first global tile id
+    uint32_t pad;
+};
+
+struct MatchArgs {
+    const uint32_t *hashes;
+    const uint64_t *ts;
+    const MatchProblem *problems;
+    const uint32_t *tile_end;   // [n_problems] exclusive end tile id per problem
+    const uint32_t *lut;        // [n_tiles >> LUT_SHIFT + 1] first problem whose tile_end > (k << LUT_SHIFT)
+    uint32_t n_tiles;
+    uint32_t threshold;
+    uint32_t run_cap;
+    // counters[0] = tile cursor, [1] = run count, [2] = error flags
+    unsigned int *counters;
+    DeviceRun *runs;
+};
+
+__device__ __forceinline__ bool hamming_match(uint32_t a, uint32_t b, uint32_t T) {
+    return (uint32_t)__popc(a ^ b) <= T;
+}
+
+// What the (rare) slow paths need; passed by value so that the kernel
+// parameter block never has its address taken.
+struct EmitCtx {
+    const uint32_t *hashes;
+    const uint64_t *ts;
+    const MatchProblem *problems;
+    unsigned int *counters;
+    DeviceRun *runs;
+    uint32_t run_cap;
+    uint32_t threshold;
+};
+
+// Exact duration filter (comparator.rs:206-223) + emission.
+__device__ __noinline__ void check_emit(const EmitCtx a, uint32_t problem, int i_end, int d, int len) {
+    const MatchProblem pr = a.problems[problem];
+    if (len < (int)pr.lcand) return;
+    const int j_end = i_end - d;
+    const uint64_t *ts_s = a.ts + pr.src_off;
+    const uint64_t *ts_d = a.ts + pr.dst_off;
+    const uint64_t s_end = ts_s[i_end], s_start = ts_s[i_end - len];
+    const uint64_t d_end = ts_d[j_end], d_start = ts_d[j_end - len];
+    if (s_end < s_start || d_end < d_start) {   // Duration - Duration panics in the reference
+        atomicOr(&a.counters[2], 1u);
+        return;
+    }
+    if (s_end - s_start >= pr.min_ns && d_end - d_start >= pr.min_ns) {
+        unsigned int slot = atomicAdd(&a.counters[1], 1u);
+        if (slot < a.run_cap) {
+            DeviceRun r;
+            r.problem = problem;
+            r.i_end = (uint32_t)i_end;
+            r.j_end = (uint32_t)j_end;
+            r.len = (uint32_t)len;
+            r.src_simhash = 0;
+            r.dst_simhash = 0;
+            a.runs[slot] = r;
+        }
+    }
+}
+
+// All maximal runs that END inside this 32-row word (i.e. are followed by a
+// non-matching cell of the word).  v: bit k = match at row i0+k.  carry = length
+// of the run active at row i0-1 (FOREIGN if it is not ours).  Returns the new
+// carry.  Slow path: only reached when a run may qualify.
+__device__ __noinline__ int runs_in_word(const EmitCtx a, uint32_t problem, uint32_t v, int carry,
+                                         int i0, int d) {
+    int pos = 0;
+    int cur = carry;
+    while (pos < 32) {
+        uint32_t rest = v >> pos;
+        uint32_t inv = ~rest;
+        int ones = inv ? (__ffs(inv) - 1) : 32;
+        if (ones > 32 - pos) ones = 32 - pos;
+        if (ones == 32 - pos) {      // run reaches the end of the word
+            cur += ones;
+            return cur;
+        }
+        int total = cur + ones;
+        if (total > 0) check_emit(a, problem, i0 + pos + ones - 1, d, total);
+        cur = 0;
+        pos += ones;
+        rest = v >> pos;             // bit 0 is now a zero
+        int zeros = rest ? (__ffs(rest) - 1) : 32;
+        pos += zeros;
+    }
+    return 0;
+}
+
+// A run we own is still active at the last row of the chunk and the cell after
+// it matches too: keep walking the diagonal in global memory until it ends.
+__device__ __noinline__ void walk_and_emit(const EmitCtx a, uint32_t problem, int i, int d, int len) {
+    const MatchProblem pr = a.problems[problem];
+    const uint32_t *hs = a.hashes + pr.src_off;
+    const uint32_t *hd = a.hashes + pr.dst_off;
+    int j = i - d;
+    // (i, j) is the first cell not yet examined
+    while (i < (int)pr.n && j < (int)pr.m && hamming_match(hs[i], hd[j], a.threshold)) {
+        len++;
+        i++;
+        j++;
+    }
+    check_emit(a, problem, i - 1, d, len);
+}
+
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchArgs a) {
+    __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][SRC_TILE];
+    __shared__ __align__(16) uint32_t s_dst[MATCH_WARPS][DST_TILE];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *src_t = s_src[warp];
+    uint32_t *dst_t = s_dst[warp];
+    const uint32_t T = a.threshold;
+    const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
+    const int ybias = -(int)(T + 1);    // popc + ybias < 0  <=>  popc <= T
+
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) break;
+
+        uint32_t p = a.lut[tile >> LUT_SHIFT];
+        while (tile >= a.tile_end[p]) p++;
+        const MatchProblem pr = a.problems[p];
+        const int n = (int)pr.n, m = (int)pr.m;
+        const uint32_t local = tile - pr.tile_begin;
+        const int chunk = (int)(local / pr.n_bands);
+        const int band = (int)(local - (uint32_t)chunk * pr.n_bands);
+        const int r0 = chunk * MATCH_R;
+        // diagonals with a valid cell in rows [r0, r0+R): d in [r0-(m-1), r0+R-2];
+        // start is lowered to == 1 (mod 4) so that tile_j0 is a multiple of 4
+        int dstart = r0 - (m - 1);
+        dstart -= (dstart - 1) & 3;
+        const int dband = dstart + band * MATCH_DW;
+        const int tile_j0 = r0 - dband - (MATCH_DW + 3);   // dst_t[s] = dst[tile_j0 + s]
+        const int tile_i0 = r0 - 4;                        // src_t[s] = src[tile_i0 + s]
+
+        // ---- stage the hash tiles (out-of-range entries are never used unmasked)
+        __syncwarp();
+        {
+            const uint32_t *hs = a.hashes + pr.src_off;
+            const uint32_t *hd = a.hashes + pr.dst_off;
+            for (int s = lane; s < SRC_TILE; s += 32) {
+                int i = tile_i0 + s;
+                src_t[s] = (i >= 0 && i < n) ? hs[i] : 0u;
+            }
+            for (int s = lane; s < DST_TILE; s += 32) {
+                int j = tile_j0 + s;
+                dst_t[s] = (j >= 0 && j < m) ? hd[j] : 0u;
+            }
+        }
+        __syncwarp();
+
+        const int dlane = dband + lane * MATCH_C;   // lane's lowest diagonal; diagonal c -> dlane + c
+        int carry[MATCH_C];
+
+        // ---- is a run already active in the row above the chunk?  (then it is not ours)
+#pragma unroll
+        for (int c = 0; c < MATCH_C; c++) {
+            const int d = dlane + c;
+            const int i = r0 - 1, j = i - d;
+            bool prev = false;
+            if (i >= 1 && j >= 1 && j <= m - 1 && i <= n - 1)
+                prev = hamming_match(src_t[i - tile_i0], dst_t[j - tile_j0], T);
+            carry[c] = prev ? FOREIGN : 0;
+        }
+
+        // ---- main loop: 32 rows x C diagonals per lane per step
+        // rows past n-1 are masked to "no match"; one (possibly all-zero) word
+        // after the last valid row closes every carry
+        const int n_steps = min(MATCH_R / 32, (n - r0) / 32 + 1);
+        for (int step = 0; step < n_steps; step++) {
+            const int i0 = r0 + step * 32;
+            // warp-uniform bounds of j over the whole warp tile at this step
+            const int jmin_w = i0 - (dband + MATCH_DW - 1);
+            const int jmax_w = i0 + 31 - dband;
+            uint32_t w[MATCH_C];
+            const bool any_valid = (jmax_w >= 1) && (jmin_w <= m - 1) && (i0 <= n - 1);
+            if (any_valid) {
+                // window of dst hashes: element e <-> dst[wbase + e], e in [0, 32+C-1)
+                const int wbase = i0 - dlane - (MATCH_C - 1);
+                const uint4 *dptr = reinterpret_cast<const uint4 *>(dst_t + (wbase - tile_j0));
+                const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + (i0 - tile_i0));
+                uint32_t dw[40];
+#pragma unroll
+                for (int q = 0; q < 10; q++) {
+                    uint4 v = dptr[q];
+                    dw[4 * q + 0] = v.x;
+                    dw[4 * q + 1] = v.y;
+                    dw[4 * q + 2] = v.z;
+                    dw[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int c = 0; c < MATCH_C; c++) w[c] = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const uint4 sv = sptr[q];
+                    const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const int k = 4 * q + kk;
+#pragma unroll
+                        for (int c = 0; c < MATCH_C; c++) {
+                            // cell (row i0+k, diagonal dlane+c): j = wbase + (C-1) + k - c
+                            const int y = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]) + ybias;
+                            // shift the sign bit of y in: row k ends up at bit 31-k
+                            w[c] = __funnelshift_l((uint32_t)y, w[c], 1);
+                        }
+                    }
+                }
+                const bool interior = (i0 >= 1) && (i0 + 31 <= n - 1) && (jmin_w >= 1) && (jmax_w <= m - 1);
+                if (!interior) {
+#pragma unroll
+                    for (int c = 0; c < MATCH_C; c++) {
+                        const int d = dlane + c;
+                        // valid rows: i in [max(1, d+1), min(n-1, d+m-1)]
+                        int klo = max(1, d + 1) - i0;
+                        int khi = min(n - 1, d + m - 1) - i0;
+                        klo = max(klo, 0);
+                        khi = min(khi, 31);
+                        uint32_t mask = 0;
+                        if (klo <= khi) {
+                            // rows klo..khi  <->  bits 31-khi .. 31-klo
+                            const uint32_t hi_part = 0xffffffffu >> klo;          // bits 31-klo .. 0
+                            const uint32_t lo_part = 0xffffffffu << (31 - khi);   // bits 31 .. 31-khi
+                            mask = hi_part & lo_part;
+                        }
+                        w[c] &= mask;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < MATCH_C; c++) w[c] = 0;
+            }
+
+            // ---- run extraction on the words
+#pragma unroll
+            for (int c = 0; c < MATCH_C; c++) {
+                const uint32_t nw = ~w[c];
+                if (nw == 0) {
+                    carry[c] += 32;
+                    continue;
+                }
+                const int lead = __clz((int)nw);       // matches in rows 0 .. lead-1
+                const bool maybe = (carry[c] + lead >= (int)pr.lcand) ||
+                                   (pr.lcand <= 30u && w[c] != 0u);
+                if (maybe) {
+                    carry[c] = runs_in_word(ectx, p, __brev(w[c]), carry[c], i0, dlane + c);
+                } else {
+                    carry[c] = __ffs((int)nw) - 1;     // matches at the end of the word
+                }
+            }
+        }
+
+        // ---- runs we own that are still active at the last row of the chunk
+        {
+            const int i = r0 + MATCH_R;    // first row after the chunk
+#pragma unroll
+            for (int c = 0; c < MATCH_C; c++) {
+                if (carry[c] > 0) {
+                    const int d = dlane + c;
+                    const int j = i - d;
+                    bool next = false;
+                    if (i <= n - 1 && j >= 1 && j <= m - 1)
+                        next = hamming_match(src_t[i - tile_i0], dst_t[j - tile_j0], T);
+                    if (!next) {
+                        if (carry[c] >= (int)pr.lcand) check_emit(ectx, p, i - 1, d, carry[c]);
+                    } else {
+                        walk_and_emit(ectx, p, i + 1, d, carry[c] + 1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// K4: simhash32 of both sides of every emitted run (comparator.rs:149-153,
+// 226-229): per-bit majority over hashes[i_end-len ..= i_end], ties -> 0.
+// One warp per run; lane b counts bit b.
+__global__ void __launch_bounds__(128) simhash_kernel(const uint32_t *__restrict__ hashes,
+                                                      const MatchProblem *__restrict__ problems,
+                                                      DeviceRun *runs, uint32_t n_runs) {
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= n_runs) return;
+    DeviceRun r = runs[warp_global];
+    const MatchProblem pr = problems[r.problem];
+    const uint32_t count = r.len + 1;
+    uint32_t out[2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const uint32_t *h = hashes + (side == 0 ? pr.src_off + (r.i_end - r.len)
+                                                : pr.dst_off + (r.j_end - r.len));
+        uint32_t ones = 0;
+        for (uint32_t base = 0; base < count; base += 32) {
+            uint32_t mine = (base + lane < count) ? h[base + lane] : 0u;
+            const uint32_t lim = min(32u, count - base);
+            for (uint32_t k = 0; k < lim; k++) {
+                uint32_t v = __shfl_sync(0xffffffffu, mine, (int)k);
+                ones += (v >> lane) & 1u;
+            }
+        }
+        // v[b] = ones - (count - ones) > 0
+        const bool bit = 2u * ones > count;
+        out[side] = __ballot_sync(0xffffffffu, bit);
+    }
+    if (lane == 0) {
+        runs[warp_global].src_simhash = out[0];
+        runs[warp_global].dst_simhash = out[1];
+    }
+}
+
+// ------------------------------------------------------------------- host
+
+static int ensure_host_ts(nb200_ctx *ctx, nb200_hashset *hs);
+
+int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pairs)[2],
+                   uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out) {
+    nb200_hashset *hs = const_cast<nb200_hashset *>(hs_c);
+    if (params->hash_match_threshold > 32) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    NB_TRY(ensure_host_ts(ctx, hs));
+
+    std::vector<uint32_t> default_flat;
+    if (!pairs) {
+        default_pairs(hs->n_videos, default_flat);
+        pairs = reinterpret_cast<const uint32_t(*)[2]>(default_flat.data());
+        n_pairs = default_flat.size() / 2;
+    }
+    const bool endings = params->include_endings != 0;
+
+    // run-length lower bounds per segment
+    const uint32_t nseg = 2 * hs->n_videos;
+    std::vector<uint32_t> lmin(nseg, 1);
+    for (uint32_t s = 0; s < nseg; s++) {
+        if ((s & 1) && !endings) continue;
+        const uint64_t mn = (s & 1) ? params->min_ending_ns : params->min_opening_ns;
+        lmin[s] = min_qualifying_len(hs->h_ts.data() + hs->seg_offset[s], hs->seg_len[s], mn);
+    }
+
+    auto rs = new nb200_runset();
+    std::vector<MatchProblem> problems;
+    problems.reserve(n_pairs * (endings ? 2 : 1));
+    uint64_t tiles = 0, cells = 0;
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        const uint32_t a = pairs[k][0], b = pairs[k][1];
+        if (a >= hs->n_videos || b >= hs->n_videos) {
+            delete rs;
+            return NB200_ERR_INVALID_ARGUMENT;
+        }
+        for (int e = 0; e < (endings ? 2 : 1); e++) {
+            const uint32_t sa = 2 * a + e, sb = 2 * b + e;
+            const uint32_t n = hs->seg_len[sa], m = hs->seg_len[sb];
+            if (e == 1 && (n == 0 || m == 0)) {   // comparator.rs:271-273
+                delete rs;
+                return NB200_ERR_NO_ENDING;
+            }
+            cells += (uint64_t)n * m;
+            if (n < 2 || m < 2) continue;   // rows/cols 0 never match: no run possible (:165-167,179)
+            MatchProblem pr;
+            pr.src_off = hs->dev_offset[sa];
+            pr.n = n;
+            pr.dst_off = hs->dev_offset[sb];
+            pr.m = m;
+            pr.min_ns = e ? params->min_ending_ns : params->min_opening_ns;
+            pr.lcand = std::max(1u, std::max(lmin[sa], lmin[sb]));
+            const uint64_t chunks = (n + MATCH_R - 1) / MATCH_R;
+            // diagonals per chunk: (m-1) + (R-1) + up to 3 of alignment slack
+            pr.n_bands = (uint32_t)(((uint64_t)m + MATCH_R + 1 + MATCH_DW - 1) / MATCH_DW);
+            pr.tile_begin = (uint32_t)tiles;
+            pr.pad = 0;
+            tiles += chunks * pr.n_bands;
+            if (tiles >= 0xfffffff0ull) {
+                delete rs;
+                return NB200_ERR_TOO_LARGE;
+            }
+            problems.push_back(pr);
+            rs->problem_pair.push_back((uint32_t)k);
+            rs->problem_is_ending.push_back((uint8_t)e);
+        }
+    }
+    rs->n_cells = cells;
+    const uint32_t n_problems = (uint32_t)problems.size();
+    const uint32_t n_tiles = (uint32_t)tiles;
+    if (n_problems == 0) {
+        *out = rs;
+        return NB200_OK;
+    }
+
+    std::vector<uint32_t> tile_end(n_problems);
+    for (uint32_t p = 0; p < n_problems; p++)
+        tile_end[p] = (p + 1 < n_problems) ? problems[p + 1].tile_begin : n_tiles;
+    const uint32_t n_lut = (n_tiles >> LUT_SHIFT) + 1;
+    std::vector<uint32_t> lut(n_lut);
+    {
+        uint32_t p = 0;
+        for (uint32_t k = 0; k < n_lut; k++) {
+            const uint32_t t = k << LUT_SHIFT;
+            while (p + 1 < n_problems && tile_end[p] <= t) p++;
+            lut[k] = p;
+        }
+    }
+
+    // upload descriptors through pinned staging
+    const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem);
+    const size_t b_tend = (size_t)n_problems * sizeof(uint32_t);
+    const size_t b_lut = (size_t)n_lut * sizeof(uint32_t);
+    auto fail = [&](int st) {
+        delete rs;
+        return st;
+    };
+    if (ctx->h_stage.reserve(b_prob + b_tend + b_lut) != NB200_OK) return fail(NB200_ERR_CUDA);
+    if (ctx->d_problems.reserve(b_prob) != NB200_OK || ctx->d_tile_end.reserve(b_tend) != NB200_OK ||
+        ctx->d_lut.reserve(b_lut) != NB200_OK || ctx->d_counters.reserve(64) != NB200_OK)
+        return fail(NB200_ERR_CUDA);
+    char *st = ctx->h_stage.as<char>();
+    memcpy(st, problems.data(), b_prob);
+    memcpy(st + b_prob, tile_end.data(), b_tend);
+    memcpy(st + b_prob + b_tend, lut.data(), b_lut);
+    cudaStream_t s = ctx->stream;
+#define NB_CUDA_F(expr)                          \
+    do {                                         \
+        cudaError_t _e = (expr);                 \
+        if (_e != cudaSuccess) {                 \
+            set_last_error(#expr, _e);           \
+            return fail(NB200_ERR_CUDA);         \
+        }                                        \
+    } while (0)
+    NB_CUDA_F(cudaMemcpyAsync(ctx->d_problems.p, st, b_prob, cudaMemcpyHostToDevice, s));
+    NB_CUDA_F(cudaMemcpyAsync(ctx->d_tile_end.p, st + b_prob, b_tend, cudaMemcpyHostToDevice, s));
+    NB_CUDA_F(cudaMemcpyAsync(ctx->d_lut.p, st + b_prob + b_tend, b_lut, cudaMemcpyHostToDevice, s));
+
+    uint32_t run_cap = std::max<uint32_t>(4096u, (uint32_t)std::min<uint64_t>(n_problems * 8ull, 1u << 22));
+    if (ctx->d_runs.bytes / sizeof(DeviceRun) > run_cap)
+        run_cap = (uint32_t)std::min<uint64_t>(ctx->d_runs.bytes / sizeof(DeviceRun), 0xffffffffull);
+    unsigned int h_counters[4];
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK) return fail(NB200_ERR_CUDA);
+        NB_CUDA_F(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
+        MatchArgs args;
+        args.hashes = hs->d_hashes.as<uint32_t>();
+        args.ts = hs->d_ts.as<uint64_t>();
+        args.problems = ctx->d_problems.as<MatchProblem>();
+        args.tile_end = ctx->d_tile_end.as<uint32_t>();
+        args.lut = ctx->d_lut.as<uint32_t>();
+        args.n_tiles = n_tiles;
+        args.threshold = params->hash_match_threshold;
+        args.run_cap = run_cap;
+        args.counters = ctx->d_counters.as<unsigned int>();
+        args.runs = ctx->d_runs.as<DeviceRun>();
+        const uint32_t warps_needed = n_tiles;
+        uint32_t grid = (uint32_t)ctx->sm_count * 4;
+        grid = std::min<uint32_t>(grid, (warps_needed + MATCH_WARPS - 1) / MATCH_WARPS);
+        NB_CUDA_F(cudaEventRecord(ctx->ev[4], s));
+        match_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        NB_CUDA_F(cudaGetLastError());
+        NB_CUDA_F(cudaEventRecord(ctx->ev[5], s));
+        ctx->ev_valid[2] = true;
+        ctx->n_launches++;
+        NB_CUDA_F(cudaMemcpyAsync(ctx->h_small.p, ctx->d_counters.p, 16, cudaMemcpyDeviceToHost, s));
+        NB_CUDA_F(cudaStreamSynchronize(s));
+        memcpy(h_counters, ctx->h_small.p, 16);
+        if (h_counters[2] & 1u) return fail(NB200_ERR_DURATION_UNDERFLOW);
+        if (h_counters[1] <= run_cap) break;
+        if (attempt == 1) return fail(NB200_ERR_TOO_LARGE);
+        run_cap = h_counters[1];     // exact count is known now: rerun with room for all of them
+    }
+    rs->n_runs = h_counters[1];
+    ctx->ev_valid[3] = false;
+    if (rs->n_runs > 0) {
+        const uint32_t nr = (uint32_t)rs->n_runs;
+        NB_CUDA_F(cudaEventRecord(ctx->ev[6], s));
+        simhash_kernel<<<(nr + 3) / 4, 128, 0, s>>>(hs->d_hashes.as<uint32_t>(),
+                                                   ctx->d_problems.as<MatchProblem>(),
+                                                   ctx->d_runs.as<DeviceRun>(), nr);
+        NB_CUDA_F(cudaGetLastError());
+        NB_CUDA_F(cudaEventRecord(ctx->ev[7], s));
+        ctx->ev_valid[3] = true;
+        ctx->n_launches++;
+        if (rs->d_runs.alloc((size_t)nr * sizeof(DeviceRun)) != NB200_OK) return fail(NB200_ERR_CUDA);
+        NB_CUDA_F(cudaMemcpyAsync(rs->d_runs.p, ctx->d_runs.p, (size_t)nr * sizeof(DeviceRun),
+                                  cudaMemcpyDeviceToDevice, s));
+    }
+#undef NB_CUDA_F
+    *out = rs;
+    return NB200_OK;
+}
+
+// Timestamps of a device-made set follow the analyzer formula; mirror them on
+// the host once (only the run-length lower bound needs them).
+static int ensure_host_ts(nb200_ctx *ctx, nb200_hashset *hs) {
+    if (hs->ts_on_host) return NB200_OK;
+    hs->h_ts.resize(hs->total);
+    // Device layout is aligned per segment: copy segment by segment.
+    std::vector<uint64_t> tmp(hs->dev_total);
+    NB_CUDA(cudaMemcpyAsync(tmp.data(), hs->d_ts.p, hs->dev_total * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < 2 * hs->n_videos; s++)
+        memcpy(hs->h_ts.data() + hs->seg_offset[s], tmp.data() + hs->dev_offset[s],
+               (size_t)hs->seg_len[s] * sizeof(uint64_t));
+    hs->ts_on_host = true;
+    return NB200_OK;
+}
+
+}  // namespace nb200
