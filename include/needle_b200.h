@@ -58,6 +58,9 @@ const char *nb200_last_error(void);
 
 /* ----------------------------------------------------------------- context */
 typedef struct nb200_ctx nb200_ctx;
+typedef struct nb200_hashset nb200_hashset; /* a season of hashes + timestamps in HBM */
+typedef struct nb200_pcmset nb200_pcmset;   /* decoded PCM segments in HBM */
+typedef struct nb200_runset nb200_runset;   /* match output in HBM */
 /* device < 0: use the calling thread's current CUDA device. */
 int nb200_ctx_create(int device, nb200_ctx **out);
 void nb200_ctx_destroy(nb200_ctx *ctx);
@@ -136,6 +139,11 @@ int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
                  const uint64_t *seg_offset, const uint64_t *hash_duration_ns, uint32_t n_videos,
                  const nb200_match_params *params, nb200_search_result *results);
 
+/* nb200_search on a season that already lives in HBM (made by
+ * nb200_fingerprint_run or nb200_hashset_from_device). */
+int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t *hash_duration_ns,
+                         const nb200_match_params *params, nb200_search_result *results);
+
 /* Host-only tail of nb200_search for callers that gathered runs themselves
  * (multi-GPU: every rank matches its share of the pair list, rank 0 votes).
  * runs must be sorted as nb200_match_pairs returns them; pairs as above. */
@@ -145,10 +153,6 @@ int nb200_vote(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *se
                uint64_t n_runs, nb200_search_result *results);
 
 /* ------------------------------------------ device-resident staged pipeline */
-
-typedef struct nb200_hashset nb200_hashset; /* a season of hashes + timestamps in HBM */
-typedef struct nb200_pcmset nb200_pcmset;   /* decoded PCM segments in HBM */
-typedef struct nb200_runset nb200_runset;   /* match output in HBM */
 
 int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
                          const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out);
@@ -160,6 +164,11 @@ int nb200_hashset_download(nb200_ctx *ctx, const nb200_hashset *hs, uint32_t *ha
 /* Raw device pointers of the packed (contiguous, seg_offset-indexed) arrays,
  * for collectives run by the host framework (e.g. NCCL all-gather). */
 int nb200_hashset_device_ptrs(const nb200_hashset *hs, void **d_hashes, void **d_ts_ns);
+/* Device-to-device copy of the set into caller-owned device arrays in the
+ * PACKED layout of nb200_hashset_upload's inputs (total u32 / total u64) --
+ * the send buffers of an all-gather. */
+int nb200_hashset_export_packed(nb200_ctx *ctx, const nb200_hashset *hs, void *d_hashes_out,
+                                void *d_ts_ns_out);
 /* Wrap device arrays already laid out like nb200_hashset_upload's inputs
  * (e.g. the result of an all-gather).  Copies device-to-device. */
 int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,

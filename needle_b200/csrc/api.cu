@@ -1,0 +1,478 @@
+// api.cu -- the C ABI of include/needle_b200.h: status/error plumbing, contexts,
+// device-resident seasons (hashsets), and the match entry points that replace
+// the pair loop of Comparator::run_with_frame_hashes
+// (needle/src/audio/comparator.rs:532-578).  The kernels live in match.cu and
+// fingerprint.cu, the host vote in vote.cpp, .needle.dat I/O in persist.cpp.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace nb200 {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const char *what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+}
+void set_last_error_msg(const std::string &msg) { g_last_error = msg; }
+
+// Packed (caller) layout -> aligned device layout, one thread per element.
+__global__ void repack_kernel(const uint32_t *__restrict__ src_h, const uint64_t *__restrict__ src_t,
+                              uint32_t *__restrict__ dst_h, uint64_t *__restrict__ dst_t,
+                              const uint64_t *__restrict__ seg_offset,
+                              const uint32_t *__restrict__ dev_offset, uint32_t n_seg, uint64_t total) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // last segment s with seg_offset[s] <= idx
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_offset[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const uint64_t o = dev_offset[lo] + (idx - seg_offset[lo]);
+    dst_h[o] = src_h[idx];
+    dst_t[o] = src_t[idx];
+}
+
+__global__ void unpack_kernel(const uint32_t *__restrict__ src_h, const uint64_t *__restrict__ src_t,
+                              uint32_t *__restrict__ dst_h, uint64_t *__restrict__ dst_t,
+                              const uint64_t *__restrict__ seg_offset,
+                              const uint32_t *__restrict__ dev_offset, uint32_t n_seg, uint64_t total) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_offset[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const uint64_t o = dev_offset[lo] + (idx - seg_offset[lo]);
+    dst_h[idx] = src_h[o];
+    dst_t[idx] = src_t[o];
+}
+
+// Fills the layout vectors of a hashset from packed offsets.
+static int layout_hashset(nb200_hashset *hs, const uint64_t *seg_offset, uint32_t n_videos) {
+    hs->n_videos = n_videos;
+    const uint32_t nseg = 2 * n_videos;
+    hs->seg_offset.assign(seg_offset, seg_offset + nseg + 1);
+    hs->dev_offset.resize(nseg);
+    hs->seg_len.resize(nseg);
+    uint64_t dev = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+        if (seg_offset[s + 1] < seg_offset[s]) return NB200_ERR_INVALID_ARGUMENT;
+        const uint64_t len = seg_offset[s + 1] - seg_offset[s];
+        if (len > 0x7fffff00ull) return NB200_ERR_TOO_LARGE;
+        hs->dev_offset[s] = (uint32_t)dev;
+        hs->seg_len[s] = (uint32_t)len;
+        dev += (len + 3) & ~3ull;
+        if (dev > 0xfffffff0ull) return NB200_ERR_TOO_LARGE;
+    }
+    hs->total = seg_offset[nseg] - seg_offset[0];
+    hs->dev_total = dev;
+    return NB200_OK;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+extern "C" {
+
+const char *nb200_status_str(int status) {
+    switch (status) {
+    case NB200_OK: return "ok";
+    case NB200_ERR_NULL_ARGUMENT: return "null argument";
+    case NB200_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case NB200_ERR_CUDA: return "CUDA error (no sm_100a device, or a runtime failure; see nb200_last_error)";
+    case NB200_ERR_NO_ENDING: return "frame hash data has no ending";
+    case NB200_ERR_DURATION_UNDERFLOW: return "timestamp subtraction underflow (the reference panics)";
+    case NB200_ERR_TOO_LARGE: return "input too large for the device layout";
+    case NB200_ERR_IO: return "I/O error";
+    case NB200_ERR_FORMAT: return "invalid frame hash data";
+    case NB200_ERR_STATE: return "call order violated";
+    case NB200_ERR_COMPARATOR_MINIMUM_PATHS: return "comparator needs at least two videos";
+    default: return "unknown status";
+    }
+}
+
+const char *nb200_last_error(void) { return g_last_error.c_str(); }
+
+/* ----------------------------------------------------------------- context */
+
+int nb200_ctx_create(int device, nb200_ctx **out) {
+    if (!out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    NB_CUDA(cudaGetDeviceCount(&count));
+    if (count <= 0) {
+        set_last_error_msg("no CUDA device");
+        return NB200_ERR_CUDA;
+    }
+    if (device < 0) NB_CUDA(cudaGetDevice(&device));
+    if (device >= count) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(device));
+    nb200_ctx *ctx = new (std::nothrow) nb200_ctx();
+    if (!ctx) return NB200_ERR_TOO_LARGE;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        set_last_error("cudaGetDeviceProperties", e);
+        delete ctx;
+        return NB200_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; ok && k < 8; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+    ok = ok && ctx->h_small.reserve(256) == NB200_OK;
+    if (!ok) {
+        set_last_error("nb200_ctx_create", cudaGetLastError());
+        nb200_ctx_destroy(ctx);
+        return NB200_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return NB200_OK;
+}
+
+void nb200_ctx_destroy(nb200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (int k = 0; k < 8; k++)
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int nb200_ctx_set_stream(nb200_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NB200_OK;
+}
+
+int nb200_ctx_synchronize(nb200_ctx *ctx) {
+    if (!ctx) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return NB200_OK;
+}
+
+int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches) {
+    if (!ctx || !ms) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; k++) {
+        ms[k] = 0.f;
+        if (ctx->ev_valid[k]) NB_CUDA(cudaEventElapsedTime(&ms[k], ctx->ev[2 * k], ctx->ev[2 * k + 1]));
+    }
+    if (n_launches) *n_launches = ctx->n_launches;
+    return NB200_OK;
+}
+
+int nb200_host_alloc(void **out, size_t bytes) {
+    if (!out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    NB_CUDA(cudaHostAlloc(out, bytes ? bytes : 16, cudaHostAllocDefault));
+    return NB200_OK;
+}
+
+int nb200_host_free(void *p) {
+    if (p) NB_CUDA(cudaFreeHost(p));
+    return NB200_OK;
+}
+
+void nb200_free(void *p) { free(p); }
+
+void nb200_match_params_default(nb200_match_params *p) {
+    if (!p) return;
+    p->hash_match_threshold = 10;          // DEFAULT_HASH_MATCH_THRESHOLD (audio/mod.rs:14)
+    p->include_endings = 0;
+    p->min_opening_ns = 20ull * 1000000000ull;   // DEFAULT_MIN_OPENING_DURATION
+    p->min_ending_ns = 20ull * 1000000000ull;    // DEFAULT_MIN_ENDING_DURATION
+    p->time_padding_ns = 0;
+}
+
+/* ----------------------------------------------------------------- hashset */
+
+int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                         const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out) {
+    if (!ctx || !seg_offset || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    if (seg_offset[0] != 0) return NB200_ERR_INVALID_ARGUMENT;
+    const uint64_t total = seg_offset[2 * (uint64_t)n_videos];
+    if (total > 0 && (!hashes || !ts_ns)) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    int st = layout_hashset(hs, seg_offset, n_videos);
+    if (st != NB200_OK) {
+        delete hs;
+        return st;
+    }
+    hs->h_ts.assign(ts_ns, ts_ns + total);
+    hs->ts_on_host = true;
+    // stage in the aligned layout (pad entries are zero and never read unmasked)
+    const size_t b_h = (size_t)hs->dev_total * sizeof(uint32_t);
+    const size_t b_t = (size_t)hs->dev_total * sizeof(uint64_t);
+    if (ctx->h_stage.reserve(b_h + b_t + 16) != NB200_OK || hs->d_hashes.alloc(b_h) != NB200_OK ||
+        hs->d_ts.alloc(b_t) != NB200_OK) {
+        delete hs;
+        return NB200_ERR_CUDA;
+    }
+    uint64_t *st_t = ctx->h_stage.as<uint64_t>();
+    uint32_t *st_h = reinterpret_cast<uint32_t *>(st_t + hs->dev_total);
+    memset(ctx->h_stage.p, 0, b_h + b_t);
+    for (uint32_t s = 0; s < 2 * n_videos; s++) {
+        memcpy(st_h + hs->dev_offset[s], hashes + seg_offset[s], (size_t)hs->seg_len[s] * sizeof(uint32_t));
+        memcpy(st_t + hs->dev_offset[s], ts_ns + seg_offset[s], (size_t)hs->seg_len[s] * sizeof(uint64_t));
+    }
+    cudaError_t e = cudaSuccess;
+    if (hs->dev_total > 0) {
+        e = cudaMemcpyAsync(hs->d_hashes.p, st_h, b_h, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hs->d_ts.p, st_t, b_t, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    // the staging buffer is reused by the next call: wait for the copies
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_last_error("nb200_hashset_upload", e);
+        delete hs;
+        return NB200_ERR_CUDA;
+    }
+    *out = hs;
+    return NB200_OK;
+}
+
+int nb200_hashset_info(const nb200_hashset *hs, uint32_t *n_videos, uint64_t *total,
+                       uint64_t *seg_offset_out) {
+    if (!hs) return NB200_ERR_NULL_ARGUMENT;
+    if (n_videos) *n_videos = hs->n_videos;
+    if (total) *total = hs->total;
+    if (seg_offset_out) memcpy(seg_offset_out, hs->seg_offset.data(), hs->seg_offset.size() * sizeof(uint64_t));
+    return NB200_OK;
+}
+
+static int pack_or_unpack(nb200_ctx *ctx, const nb200_hashset *hs, bool to_packed, const void *src_h,
+                          const void *src_t, void *dst_h, void *dst_t) {
+    // device copies of the two offset tables
+    const uint32_t nseg = 2 * hs->n_videos;
+    DevBuf d_off, d_dev;
+    NB_TRY(d_off.alloc((nseg + 1) * sizeof(uint64_t)));
+    NB_TRY(d_dev.alloc(std::max<uint32_t>(nseg, 1) * sizeof(uint32_t)));
+    NB_CUDA(cudaMemcpyAsync(d_off.p, hs->seg_offset.data(), (nseg + 1) * sizeof(uint64_t),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(d_dev.p, hs->dev_offset.data(), nseg * sizeof(uint32_t),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t total = hs->total;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (to_packed)
+        unpack_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t *)src_h, (const uint64_t *)src_t,
+                                                     (uint32_t *)dst_h, (uint64_t *)dst_t,
+                                                     d_off.as<uint64_t>(), d_dev.as<uint32_t>(), nseg, total);
+    else
+        repack_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t *)src_h, (const uint64_t *)src_t,
+                                                     (uint32_t *)dst_h, (uint64_t *)dst_t,
+                                                     d_off.as<uint64_t>(), d_dev.as<uint32_t>(), nseg, total);
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));   // d_off / d_dev die here
+    return NB200_OK;
+}
+
+int nb200_hashset_download(nb200_ctx *ctx, const nb200_hashset *hs, uint32_t *hashes_out,
+                           uint64_t *ts_ns_out) {
+    if (!ctx || !hs) return NB200_ERR_NULL_ARGUMENT;
+    if (hs->total == 0) return NB200_OK;
+    if (!hashes_out || !ts_ns_out) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> th(hs->dev_total);
+    std::vector<uint64_t> tt(hs->dev_total);
+    NB_CUDA(cudaMemcpyAsync(th.data(), hs->d_hashes.p, hs->dev_total * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(tt.data(), hs->d_ts.p, hs->dev_total * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < 2 * hs->n_videos; s++) {
+        memcpy(hashes_out + hs->seg_offset[s], th.data() + hs->dev_offset[s],
+               (size_t)hs->seg_len[s] * sizeof(uint32_t));
+        memcpy(ts_ns_out + hs->seg_offset[s], tt.data() + hs->dev_offset[s],
+               (size_t)hs->seg_len[s] * sizeof(uint64_t));
+    }
+    return NB200_OK;
+}
+
+int nb200_hashset_export_packed(nb200_ctx *ctx, const nb200_hashset *hs, void *d_hashes_out,
+                                void *d_ts_ns_out) {
+    if (!ctx || !hs) return NB200_ERR_NULL_ARGUMENT;
+    if (hs->total == 0) return NB200_OK;
+    if (!d_hashes_out || !d_ts_ns_out) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    return pack_or_unpack(ctx, hs, true, hs->d_hashes.p, hs->d_ts.p, d_hashes_out, d_ts_ns_out);
+}
+
+int nb200_hashset_device_ptrs(const nb200_hashset *hs, void **d_hashes, void **d_ts_ns) {
+    if (!hs) return NB200_ERR_NULL_ARGUMENT;
+    if (d_hashes) *d_hashes = hs->d_hashes.p;
+    if (d_ts_ns) *d_ts_ns = hs->d_ts.p;
+    return NB200_OK;
+}
+
+int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                              const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out) {
+    if (!ctx || !seg_offset || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    if (seg_offset[0] != 0) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    int st = layout_hashset(hs, seg_offset, n_videos);
+    if (st == NB200_OK && hs->total > 0 && (!d_hashes || !d_ts_ns)) st = NB200_ERR_NULL_ARGUMENT;
+    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t));
+    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t));
+    if (st == NB200_OK && hs->dev_total > 0) {
+        cudaError_t e = cudaMemsetAsync(hs->d_hashes.p, 0, hs->dev_total * sizeof(uint32_t), ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(hs->d_ts.p, 0, hs->dev_total * sizeof(uint64_t), ctx->stream);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMemsetAsync", e);
+            st = NB200_ERR_CUDA;
+        }
+    }
+    if (st == NB200_OK && hs->total > 0)
+        st = pack_or_unpack(ctx, hs, false, d_hashes, d_ts_ns, hs->d_hashes.p, hs->d_ts.p);
+    if (st != NB200_OK) {
+        delete hs;
+        return st;
+    }
+    hs->ts_on_host = false;   // mirrored lazily by the match stage
+    *out = hs;
+    return NB200_OK;
+}
+
+void nb200_hashset_free(nb200_hashset *hs) { delete hs; }
+
+/* ------------------------------------------------------------------- match */
+
+int nb200_match_run(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
+                    uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out) {
+    if (!ctx || !hs || !params || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    return match_run_impl(ctx, hs, pairs, n_pairs, params, out);
+}
+
+int nb200_runset_count(const nb200_runset *rs, uint64_t *n_runs, uint64_t *n_cells) {
+    if (!rs) return NB200_ERR_NULL_ARGUMENT;
+    if (n_runs) *n_runs = rs->n_runs;
+    if (n_cells) *n_cells = rs->n_cells;
+    return NB200_OK;
+}
+
+int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *runs_out) {
+    if (!ctx || !rs) return NB200_ERR_NULL_ARGUMENT;
+    if (rs->n_runs == 0) return NB200_OK;
+    if (!runs_out) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<DeviceRun> tmp(rs->n_runs);
+    NB_CUDA(cudaMemcpyAsync(tmp.data(), rs->d_runs.p, rs->n_runs * sizeof(DeviceRun),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the reference's push order: pair, opening before ending, i desc, j desc
+    // (problems are numbered in (pair, is_ending) order)
+    std::sort(tmp.begin(), tmp.end(), [](const DeviceRun &a, const DeviceRun &b) {
+        if (a.problem != b.problem) return a.problem < b.problem;
+        if (a.i_end != b.i_end) return a.i_end > b.i_end;
+        return a.j_end > b.j_end;
+    });
+    for (uint64_t k = 0; k < rs->n_runs; k++) {
+        const DeviceRun &r = tmp[k];
+        nb200_run &o = runs_out[k];
+        o.pair = rs->problem_pair[r.problem];
+        o.is_ending = rs->problem_is_ending[r.problem];
+        o.i_end = r.i_end;
+        o.j_end = r.j_end;
+        o.len = r.len;
+        o.src_simhash = r.src_simhash;
+        o.dst_simhash = r.dst_simhash;
+        o.reserved = 0;
+    }
+    return NB200_OK;
+}
+
+void nb200_runset_free(nb200_runset *rs) { delete rs; }
+
+int nb200_match_pairs(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                      const uint64_t *seg_offset, uint32_t n_videos, const uint32_t (*pairs)[2],
+                      uint64_t n_pairs, const nb200_match_params *params, nb200_run **out_runs,
+                      uint64_t *out_n) {
+    if (!ctx || !seg_offset || !params || !out_runs || !out_n) return NB200_ERR_NULL_ARGUMENT;
+    *out_runs = nullptr;
+    *out_n = 0;
+    nb200_hashset *hs = nullptr;
+    NB_TRY(nb200_hashset_upload(ctx, hashes, ts_ns, seg_offset, n_videos, &hs));
+    nb200_runset *rs = nullptr;
+    int st = nb200_match_run(ctx, hs, pairs, n_pairs, params, &rs);
+    if (st == NB200_OK) {
+        nb200_run *runs = (nb200_run *)malloc(std::max<uint64_t>(rs->n_runs, 1) * sizeof(nb200_run));
+        if (!runs) st = NB200_ERR_TOO_LARGE;
+        if (st == NB200_OK) st = nb200_runset_download(ctx, rs, runs);
+        if (st == NB200_OK) {
+            *out_runs = runs;
+            *out_n = rs->n_runs;
+        } else {
+            free(runs);
+        }
+    }
+    nb200_runset_free(rs);
+    nb200_hashset_free(hs);
+    return st;
+}
+
+int nb200_vote(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
+               const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
+               uint64_t n_runs, nb200_search_result *results) {
+    if (!seg_offset || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_runs > 0 && (!runs || !ts_ns)) return NB200_ERR_NULL_ARGUMENT;
+    return vote_impl(hashes, ts_ns, seg_offset, hash_duration_ns, n_videos, pairs, n_pairs, params, runs,
+                     n_runs, results);
+}
+
+int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
+                 const uint64_t *seg_offset, const uint64_t *hash_duration_ns, uint32_t n_videos,
+                 const nb200_match_params *params, nb200_search_result *results) {
+    if (!ctx || !seg_offset || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_videos < 2) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;   // main.rs:305-315, capi lib.rs:569
+    nb200_run *runs = nullptr;
+    uint64_t n_runs = 0;
+    NB_TRY(nb200_match_pairs(ctx, hashes, ts_ns, seg_offset, n_videos, nullptr, 0, params, &runs, &n_runs));
+    int st = vote_impl(hashes, ts_ns, seg_offset, hash_duration_ns, n_videos, nullptr, 0, params, runs,
+                       n_runs, results);
+    free(runs);
+    return st;
+}
+
+/* --------------------------------------------------------------- searching
+ * a device-resident season (the tail of nb200_analyze_search and of the
+ * multi-GPU flow): match on the GPU, download runs + timestamps, vote. */
+int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t *hash_duration_ns,
+                         const nb200_match_params *params, nb200_search_result *results) {
+    if (!ctx || !hs || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (hs->n_videos < 2) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;
+    nb200_runset *rs = nullptr;
+    NB_TRY(nb200_match_run(ctx, hs, nullptr, 0, params, &rs));
+    std::vector<nb200_run> runs(std::max<uint64_t>(rs->n_runs, 1));
+    int st = nb200_runset_download(ctx, rs, runs.data());
+    // match_run_impl mirrored the timestamps on the host already
+    if (st == NB200_OK)
+        st = vote_impl(nullptr, hs->h_ts.data(), hs->seg_offset.data(), hash_duration_ns, hs->n_videos,
+                       nullptr, 0, params, runs.data(), rs->n_runs, results);
+    nb200_runset_free(rs);
+    return st;
+}
+
+}  // extern "C"

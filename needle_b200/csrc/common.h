@@ -93,6 +93,10 @@ struct nb200_ctx {
     // scratch reused across calls
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_runs_sorted;
     nb200::PinnedBuf h_stage, h_small;
+    // fingerprint stage: constant tables (built once per context) and scratch
+    bool fp_ready = false;
+    nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
+    nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
 
 // Device layout of a season: every segment starts at a multiple of 4 elements
@@ -119,10 +123,10 @@ struct nb200_hashset {
 
 struct nb200_pcmset {
     uint32_t n_segments = 0;
-    int channels = 1;
-    std::vector<uint64_t> n_frames_pcm;   // mono sample count per segment
+    std::vector<uint64_t> n_mono;         // mono sample count per segment
     std::vector<uint64_t> dev_offset;     // element (i16) offset of each segment, 8-aligned
-    nb200::DevBuf d_pcm;
+    uint64_t dev_total = 0;
+    nb200::DevBuf d_pcm;                  // mono i16 (stereo input is down-mixed on upload)
 };
 
 struct nb200_runset {

@@ -1,0 +1,870 @@
+// fingerprint.cu -- K1/K2: Chromaprint-style frame hashing on sm_100a.
+//
+// Replaces the chromaprint::Context that Analyzer::process_frames drives
+// (needle/src/audio/analyzer.rs:176,218,275,286-301: start / feed / finish /
+// get_fingerprint_raw) plus the subsample-and-stamp tail (:288-318).  The
+// algorithm is Chromaprint 1.5.x TEST2 (crate chromaprint-sys-next 1.5.3,
+// needle/Cargo.lock:158-159); constants in fp_tables.h.
+//
+// K1 fp_fft_chroma: one WARP per 4096-sample frame (hop 1365).  The real FFT is
+// a 2048-point complex FFT of z[n] = x[2n] + i x[2n+1] plus a split step:
+//   pass 1  lane L holds z[32 m + L], m = 0..63 (coalesced loads, window
+//           fused); 64-point FFT over m entirely in registers (8 x 8)
+//   xchg    one transpose through shared memory (padded, conflict-free)
+//   pass 2  lane L holds k1 in {L, L+32}: twiddle, two 32-point FFTs in
+//           registers (8 x 4)  ->  Z[L + 32 t], t = 0..63
+//   split   Z[2048-k] lives in lane (32-L)&31: one warp shuffle per value;
+//           power |X[k]|^2 for k in [10, 1308), folded into 12 pitch classes
+// Output: 12 floats per frame.  FP32 throughout.
+//
+// K2 fp_classify: FIR {.25,.75,1,.75,.25} over time, L2 normalisation, the
+// 16 Haar-like classifiers on each 16-row window via a tile-local integral
+// image, 3-threshold quantisation, Gray code, packing, stride-s emission and
+// the timestamp.  All in FP64: it is <1 % of the work, and FP32 would flip
+// hashes near quantiser thresholds.  log((1+a)/(1+b)) < t is evaluated as
+// (1+a) < e^t (1+b).
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.h"
+#include "fp_tables.h"
+
+namespace nb200 {
+
+constexpr int FP_WARPS = 8;                 // frames in flight per CTA
+constexpr int FP_HALF = FP_FRAME / 2;       // 2048-point complex FFT
+constexpr int XCHG_STRIDE = 33;             // float2 row stride of the transpose buffer
+constexpr int XCHG_ELEMS = 64 * XCHG_STRIDE;
+constexpr int FP_KMIN = 10, FP_KMAX = 1308; // chroma bins [10, 1308)
+constexpr int FP_T = 41;                    // k = L + 32 t covers [0, 1312)
+constexpr int K2_TILE = 128;                // raw hashes per CTA
+constexpr int K2_ROWS = K2_TILE + FP_WINDOW_ROWS - 1;   // 143 normalised rows
+constexpr int K2_COLS = FP_BANDS + 1;
+
+__constant__ float2 c_w64[64];    // exp(-2 pi i e / 64)
+__constant__ float2 c_w32[32];    // exp(-2 pi i e / 32)
+__constant__ float2 c_w128[FP_T]; // exp(-2 pi i t / 128) = W_4096^(32 t)
+
+struct K2Classifier {
+    int type, y, h, w;
+    double e0, e1, e2;   // exp(t0), exp(t1), exp(t2)
+};
+__constant__ K2Classifier c_cls[FP_NUM_CLASSIFIERS];
+__constant__ double c_fir[FP_FIR_LEN];
+
+uint64_t num_frames(uint64_t n_mono) {
+    return n_mono >= (uint64_t)FP_FRAME ? (n_mono - FP_FRAME) / FP_HOP + 1 : 0;
+}
+static uint64_t num_raw(uint64_t n_mono) {
+    const uint64_t f = num_frames(n_mono);
+    return f > (uint64_t)FP_WARMUP ? f - FP_WARMUP : 0;
+}
+
+// ------------------------------------------------------------ complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // * (-i)
+
+// Forward DFTs on register arrays; S = element stride.  Natural order in and out.
+template <int S> __device__ __forceinline__ void fft4(float2 *v) {
+    const float2 c0 = v[0], c1 = v[S], c2 = v[2 * S], c3 = v[3 * S];
+    const float2 d0 = cadd(c0, c2), d1 = csub(c0, c2), d2 = cadd(c1, c3), d3 = mul_mi(csub(c1, c3));
+    v[0] = cadd(d0, d2);
+    v[S] = cadd(d1, d3);
+    v[2 * S] = csub(d0, d2);
+    v[3 * S] = csub(d1, d3);
+}
+
+template <int S> __device__ __forceinline__ void fft8(float2 *v) {
+    constexpr float R = 0.70710678118654752440f;
+    const float2 a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S];
+    const float2 a4 = v[4 * S], a5 = v[5 * S], a6 = v[6 * S], a7 = v[7 * S];
+    // X[2r] = FFT4(a_j + a_{j+4}),  X[2r+1] = FFT4((a_j - a_{j+4}) W8^j)
+    const float2 b0 = cadd(a0, a4), b1 = cadd(a1, a5), b2 = cadd(a2, a6), b3 = cadd(a3, a7);
+    const float2 b4 = csub(a0, a4);
+    const float2 t5 = csub(a1, a5), t7 = csub(a3, a7);
+    const float2 b5 = make_float2((t5.x + t5.y) * R, (t5.y - t5.x) * R);     // * (1 - i)/sqrt2
+    const float2 b6 = mul_mi(csub(a2, a6));
+    const float2 b7 = make_float2((t7.y - t7.x) * R, -(t7.x + t7.y) * R);    // * (-1 - i)/sqrt2
+    {
+        const float2 d0 = cadd(b0, b2), d1 = csub(b0, b2), d2 = cadd(b1, b3), d3 = mul_mi(csub(b1, b3));
+        v[0] = cadd(d0, d2);
+        v[2 * S] = cadd(d1, d3);
+        v[4 * S] = csub(d0, d2);
+        v[6 * S] = csub(d1, d3);
+    }
+    {
+        const float2 d0 = cadd(b4, b6), d1 = csub(b4, b6), d2 = cadd(b5, b7), d3 = mul_mi(csub(b5, b7));
+        v[S] = cadd(d0, d2);
+        v[3 * S] = cadd(d1, d3);
+        v[5 * S] = csub(d0, d2);
+        v[7 * S] = csub(d1, d3);
+    }
+}
+
+// 64-point FFT, n = n1 + 8 n2, k = 8 k1 + k2: X[8 k1 + k2] ends up at v[k1 + 8 k2].
+__device__ __forceinline__ void fft64(float2 *v) {
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) fft8<8>(v + n1);
+#pragma unroll
+    for (int n1 = 1; n1 < 8; n1++)
+#pragma unroll
+        for (int k2 = 1; k2 < 8; k2++) v[n1 + 8 * k2] = cmul(v[n1 + 8 * k2], c_w64[n1 * k2]);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) fft8<1>(v + 8 * k2);
+}
+__device__ __forceinline__ constexpr int pos64(int k) { return (k >> 3) + 8 * (k & 7); }
+
+// 32-point FFT, n = n1 + 8 n2 (n2 < 4), k = 4 k1 + k2: X[4 k1 + k2] at v[k1 + 8 k2].
+__device__ __forceinline__ void fft32(float2 *v) {
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) fft4<8>(v + n1);
+#pragma unroll
+    for (int n1 = 1; n1 < 8; n1++)
+#pragma unroll
+        for (int k2 = 1; k2 < 4; k2++) v[n1 + 8 * k2] = cmul(v[n1 + 8 * k2], c_w32[n1 * k2]);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) fft8<1>(v + 8 * k2);
+}
+__device__ __forceinline__ constexpr int pos32(int k) { return (k >> 2) + 8 * (k & 3); }
+// register slot of Z[L + 32 t]: k1 = L + 32 (t & 1), k2 = t >> 1
+__device__ __forceinline__ constexpr int zslot(int t) { return (t & 1) * 32 + pos32(t >> 1); }
+
+// two packed i16 -> two floats without I2F: 0x4B00hhhh is 2^23 + hhhh
+__device__ __forceinline__ float2 s16x2_to_float(uint32_t w) {
+    w ^= 0x80008000u;   // bias to unsigned
+    const float lo = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8421376.0f;
+    const float hi = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8421376.0f;
+    return make_float2(lo, hi);
+}
+
+struct FpSegment {
+    uint64_t pcm_off;      // element offset of the segment's mono PCM
+    uint32_t frame_begin;  // first global frame index
+    uint32_t n_frames;
+    uint32_t n_raw;        // raw sub-fingerprints = n_frames - 19
+    uint32_t tile_begin;   // first K2 tile
+    uint32_t out_off;      // element offset into the hashset arrays
+    uint32_t pad;
+    uint64_t seek_to_ns;
+};
+
+struct K1Args {
+    const int16_t *pcm;
+    const FpSegment *segs;
+    uint32_t n_segs;
+    uint32_t total_frames;
+    const float2 *window;    // [2048]  (w[2n], w[2n+1]) / 32767
+    const float2 *twiddle;   // [32][64] W_2048^(n2 k1)
+    const float2 *lane_w;    // [32] W_4096^L
+    const uint32_t *notes;   // [6][32] 4-bit pitch class of bin L + 32 t (12 = unused)
+    float *chroma;           // [total_frames][12]
+};
+
+__global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K1Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *s_window = reinterpret_cast<float2 *>(smem_raw);           // 2048
+    float2 *s_twiddle = s_window + FP_HALF;                            // 2048
+    float2 *s_xchg_all = s_twiddle + FP_HALF;                          // FP_WARPS * XCHG_ELEMS
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
+        s_window[i] = a.window[i];
+        s_twiddle[i] = a.twiddle[i];
+    }
+    __syncthreads();
+
+    float2 *xchg = s_xchg_all + warp * XCHG_ELEMS;
+    float *acc = reinterpret_cast<float *>(xchg);     // [13][32], reused after pass 2
+    const int partner = (32 - lane) & 31;
+    const float2 lane_w = a.lane_w[lane];
+    uint32_t notes[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) notes[q] = a.notes[q * 32 + lane];
+
+    const uint32_t n_blocks = (a.total_frames + FP_WARPS - 1) / FP_WARPS;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t frame = blk * FP_WARPS + warp;
+        if (frame >= a.total_frames) continue;   // warp-uniform; no block barrier below
+        // segment of this frame: last s with frame_begin <= frame
+        uint32_t lo = 0, hi = a.n_segs;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (a.segs[mid].frame_begin <= frame) lo = mid; else hi = mid;
+        }
+        const FpSegment sg = a.segs[lo];
+        const int16_t *src = a.pcm + sg.pcm_off + (uint64_t)(frame - sg.frame_begin) * FP_HOP;
+
+        float2 v[64];
+        // ---- load + window: z[32 m + L] = (x[2n] w[2n], x[2n+1] w[2n+1])
+        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + lane;
+#pragma unroll
+            for (int m = 0; m < 64; m++) {
+                const float2 s = s16x2_to_float(__ldg(p + 32 * m));
+                const float2 w = s_window[32 * m + lane];
+                v[m] = make_float2(s.x * w.x, s.y * w.y);
+            }
+        } else {
+            const uint16_t *p = reinterpret_cast<const uint16_t *>(src) + 2 * lane;
+#pragma unroll
+            for (int m = 0; m < 64; m++) {
+                const uint32_t wlo = __ldg(p + 64 * m), whi = __ldg(p + 64 * m + 1);
+                const float2 s = s16x2_to_float(wlo | (whi << 16));
+                const float2 w = s_window[32 * m + lane];
+                v[m] = make_float2(s.x * w.x, s.y * w.y);
+            }
+        }
+
+        // ---- pass 1: 64-point FFT over m; Y[k1] (for n2 = L) at v[pos64(k1)]
+        fft64(v);
+
+        // ---- transpose: S[k1][n2]
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 64; k1++) xchg[k1 * XCHG_STRIDE + lane] = v[pos64(k1)];
+        __syncwarp();
+        // ---- pass 2: lane holds k1 = L + 32 q; twiddle W_2048^(n2 k1); 32-point FFT over n2
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++)
+                v[q * 32 + n2] = cmul(xchg[(lane + 32 * q) * XCHG_STRIDE + n2],
+                                      s_twiddle[n2 * 64 + lane + 32 * q]);
+        __syncwarp();
+        fft32(v);
+        fft32(v + 32);
+        // now Z[L + 32 t] = v[zslot(t)]
+
+        // ---- split + power + chroma fold
+#pragma unroll
+        for (int r = 0; r < 13; r++) acc[r * 32 + lane] = 0.f;
+#pragma unroll
+        for (int t = 0; t < FP_T; t++) {
+            const float2 z = v[zslot(t)];
+            const float2 ps = v[zslot(63 - t)];
+            float2 zp;
+            zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
+            zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
+            if (t >= 1) {   // lane 0 pairs k = 32 t with 2048 - 32 t, which it holds itself
+                const float2 own = v[zslot(t >= 1 ? 64 - t : 0)];
+                if (lane == 0) zp = own;
+            }
+            // 2E = (a+c, b-d), 2O = (b+d, -(a-c)) with Z[k] = a+ib, Z[N-k] = c+id
+            const float er = z.x + zp.x, ei = z.y - zp.y;
+            const float orr = z.y + zp.y, oi = zp.x - z.x;
+            const float2 w = cmul(lane_w, c_w128[t]);            // W_4096^(L + 32 t)
+            const float xr = er + (orr * w.x - oi * w.y);
+            const float xi = ei + (orr * w.y + oi * w.x);
+            const float pw = 0.25f * (xr * xr + xi * xi);
+            const uint32_t note = (notes[t >> 3] >> (4 * (t & 7))) & 15u;
+            acc[note * 32 + lane] += pw;
+        }
+        __syncwarp();
+        float sums[FP_BANDS];
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) {
+            float s = acc[b * 32 + lane];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            sums[b] = s;
+        }
+        if (lane == 0) {
+            float4 *out = reinterpret_cast<float4 *>(a.chroma + (uint64_t)frame * FP_BANDS);
+            out[0] = make_float4(sums[0], sums[1], sums[2], sums[3]);
+            out[1] = make_float4(sums[4], sums[5], sums[6], sums[7]);
+            out[2] = make_float4(sums[8], sums[9], sums[10], sums[11]);
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------- K2
+
+struct K2Args {
+    const float *chroma;
+    const FpSegment *segs;
+    uint32_t n_segs;
+    uint32_t n_tiles;
+    uint32_t stride;
+    float item_secs;        // Duration::as_secs_f32(item_duration)
+    uint64_t delay_ns;
+    uint32_t *out_hash;
+    uint64_t *out_ts;
+};
+
+__device__ __forceinline__ double area(const double *I, int r1, int c1, int r2, int c2) {
+    return I[r2 * K2_COLS + c2] - I[r1 * K2_COLS + c2] - I[r2 * K2_COLS + c1] + I[r1 * K2_COLS + c1];
+}
+
+__global__ void __launch_bounds__(K2_TILE) fp_classify_kernel(const K2Args a) {
+    // I[r][c] = sum of rows < r, columns < c of the tile's normalised rows
+    __shared__ double I[(K2_ROWS + 1) * K2_COLS];
+    const uint32_t tile = blockIdx.x;
+    uint32_t lo = 0, hi = a.n_segs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.segs[mid].tile_begin <= tile) lo = mid; else hi = mid;
+    }
+    const FpSegment sg = a.segs[lo];
+    const uint32_t x0 = (tile - sg.tile_begin) * K2_TILE;
+    const int n_here = (int)min((uint32_t)K2_TILE, sg.n_raw - x0);
+    const int n_rows = n_here + FP_WINDOW_ROWS - 1;
+    const int tid = threadIdx.x;
+
+    for (int c = tid; c < K2_COLS; c += K2_TILE) I[c] = 0.0;
+    for (int r = tid; r < n_rows; r += K2_TILE) {
+        // ChromaFilter: row r of the tile = frames x0+r .. x0+r+4
+        const float *f = a.chroma + ((uint64_t)sg.frame_begin + x0 + r) * FP_BANDS;
+        double y[FP_BANDS];
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < FP_FIR_LEN; j++) s += (double)f[j * FP_BANDS + b] * c_fir[j];
+            y[b] = s;
+        }
+        // ChromaNormalizer: Euclidean norm, zero below the threshold
+        double sq = 0.0;
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) sq += y[b] * y[b];
+        const double norm = sqrt(sq);
+        double *row = I + (r + 1) * K2_COLS;
+        row[0] = 0.0;
+        double run = 0.0;
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) {
+            const double val = norm < FP_NORM_THRESHOLD ? 0.0 : y[b] / norm;
+            run += val;
+            row[b + 1] = run;   // prefix along the pitch classes
+        }
+    }
+    __syncthreads();
+    if (tid >= 1 && tid < K2_COLS) {   // prefix along time, one thread per column
+        double run = 0.0;
+        for (int r = 1; r <= n_rows; r++) {
+            run += I[r * K2_COLS + tid];
+            I[r * K2_COLS + tid] = run;
+        }
+    }
+    __syncthreads();
+    if (tid >= n_here) return;
+
+    const int x = tid;   // window = rows [x, x+16) of the tile
+    uint32_t bits = 0;
+#pragma unroll 1
+    for (int k = 0; k < FP_NUM_CLASSIFIERS; k++) {
+        const K2Classifier cl = c_cls[k];
+        const int y = cl.y, h = cl.h, w = cl.w;
+        double pa, pb;
+        switch (cl.type) {
+        case 0:
+            pa = area(I, x, y, x + w, y + h);
+            pb = 0.0;
+            break;
+        case 1: {
+            const int h2 = h / 2;
+            pa = area(I, x, y + h2, x + w, y + h);
+            pb = area(I, x, y, x + w, y + h2);
+            break;
+        }
+        case 2: {
+            const int w2 = w / 2;
+            pa = area(I, x + w2, y, x + w, y + h);
+            pb = area(I, x, y, x + w2, y + h);
+            break;
+        }
+        case 3: {
+            const int w2 = w / 2, h2 = h / 2;
+            pa = area(I, x, y + h2, x + w2, y + h) + area(I, x + w2, y, x + w, y + h2);
+            pb = area(I, x, y, x + w2, y + h2) + area(I, x + w2, y + h2, x + w, y + h);
+            break;
+        }
+        case 4: {
+            const int h3 = h / 3;
+            pa = area(I, x, y + h3, x + w, y + 2 * h3);
+            pb = area(I, x, y, x + w, y + h3) + area(I, x, y + 2 * h3, x + w, y + h);
+            break;
+        }
+        default: {
+            const int w3 = w / 3;
+            pa = area(I, x + w3, y, x + 2 * w3, y + h);
+            pb = area(I, x, y, x + w3, y + h) + area(I, x + 2 * w3, y, x + w, y + h);
+            break;
+        }
+        }
+        // Quantizer on log((1+a)/(1+b)), evaluated without the log
+        const double num = 1.0 + pa, den = 1.0 + pb;
+        int q;
+        if (num < cl.e1 * den) q = num < cl.e0 * den ? 0 : 1;
+        else q = num < cl.e2 * den ? 2 : 3;
+        const uint32_t gray = (uint32_t)(q ^ (q >> 1));   // {0,1,3,2}
+        bits = (bits << 2) | gray;
+    }
+    const uint32_t raw_idx = x0 + (uint32_t)x;
+    if (raw_idx % a.stride == 0) {
+        const uint32_t o = sg.out_off + raw_idx / a.stride;
+        a.out_hash[o] = bits;
+        // ts = delay + item.mul_f32(i as f32) + seek_to   (analyzer.rs:309,314-318)
+        const float p = __fmul_rn(__uint2float_rn(raw_idx), a.item_secs);
+        a.out_ts[o] = a.delay_ns + __double2ull_rn((double)p * 1e9) + sg.seek_to_ns;
+    }
+}
+
+// (L + R) / 2 with C integer division, as Chromaprint's AudioProcessor::LoadStereo
+__global__ void downmix_kernel(const int16_t *__restrict__ stereo, int16_t *__restrict__ mono, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int l = stereo[2 * i], r = stereo[2 * i + 1];
+    mono[i] = (int16_t)((l + r) / 2);
+}
+
+// ------------------------------------------------------------------- host
+
+static float as_secs_f32(uint64_t ns) {
+    volatile float s = (float)(ns / 1000000000ull);
+    volatile float f = (float)(uint32_t)(ns % 1000000000ull) / 1000000000.0f;
+    return s + f;
+}
+
+static int ensure_fp_tables(nb200_ctx *ctx) {
+    if (ctx->fp_ready) return NB200_OK;
+    const double PI = 3.14159265358979323846;
+    std::vector<float2> window(FP_HALF), tw(FP_HALF), lane_w(32), w64(64), w32(32), w128(FP_T);
+    for (int n = 0; n < FP_HALF; n++) {
+        // PrepareHammingWindow(first, last, 1.0 / INT16_MAX)
+        const double w0 = (1.0 / 32767.0) * (0.54 - 0.46 * cos((2 * n) * 2.0 * PI / (FP_FRAME - 1)));
+        const double w1 = (1.0 / 32767.0) * (0.54 - 0.46 * cos((2 * n + 1) * 2.0 * PI / (FP_FRAME - 1)));
+        window[n] = make_float2((float)w0, (float)w1);
+    }
+    for (int n2 = 0; n2 < 32; n2++)
+        for (int k1 = 0; k1 < 64; k1++) {
+            const double ang = -2.0 * PI * (double)(n2 * k1) / FP_HALF;
+            tw[n2 * 64 + k1] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    for (int l = 0; l < 32; l++) {
+        const double ang = -2.0 * PI * l / FP_FRAME;
+        lane_w[l] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (int e = 0; e < 64; e++) w64[e] = make_float2((float)cos(-2.0 * PI * e / 64), (float)sin(-2.0 * PI * e / 64));
+    for (int e = 0; e < 32; e++) w32[e] = make_float2((float)cos(-2.0 * PI * e / 32), (float)sin(-2.0 * PI * e / 32));
+    for (int t = 0; t < FP_T; t++)
+        w128[t] = make_float2((float)cos(-2.0 * PI * t / 128), (float)sin(-2.0 * PI * t / 128));
+
+    // Chroma::PrepareNotes: bins [min_index, max_index) -> pitch class
+    const int min_index = std::max(1, (int)lround((double)FP_FRAME * FP_MIN_FREQ / FP_SAMPLE_RATE));
+    const int max_index = std::min(FP_FRAME / 2, (int)lround((double)FP_FRAME * FP_MAX_FREQ / FP_SAMPLE_RATE));
+    if (min_index != FP_KMIN || max_index != FP_KMAX) {
+        set_last_error_msg("chroma bin range does not match the kernel's compiled range");
+        return NB200_ERR_STATE;
+    }
+    std::vector<uint32_t> notes(6 * 32, 0);
+    for (int l = 0; l < 32; l++)
+        for (int t = 0; t < 48; t++) {
+            const int k = l + 32 * t;
+            uint32_t note = 12;
+            if (t < FP_T && k >= min_index && k < max_index) {
+                const double freq = (double)k * FP_SAMPLE_RATE / FP_FRAME;
+                const double octave = log(freq / (440.0 / 16.0)) / log(2.0);
+                note = (uint32_t)(int)(FP_BANDS * (octave - floor(octave)));
+            }
+            notes[(t >> 3) * 32 + l] |= note << (4 * (t & 7));
+        }
+
+    K2Classifier cls[FP_NUM_CLASSIFIERS];
+    for (int k = 0; k < FP_NUM_CLASSIFIERS; k++) {
+        const FpClassifierDef &d = FP_CLASSIFIERS_TEST2[k];
+        cls[k] = {d.type, d.y, d.height, d.width, exp(d.t0), exp(d.t1), exp(d.t2)};
+    }
+    NB_CUDA(cudaMemcpyToSymbol(c_w64, w64.data(), sizeof(float2) * 64));
+    NB_CUDA(cudaMemcpyToSymbol(c_w32, w32.data(), sizeof(float2) * 32));
+    NB_CUDA(cudaMemcpyToSymbol(c_w128, w128.data(), sizeof(float2) * FP_T));
+    NB_CUDA(cudaMemcpyToSymbol(c_cls, cls, sizeof(cls)));
+    NB_CUDA(cudaMemcpyToSymbol(c_fir, FP_FIR_COEFFS, sizeof(double) * FP_FIR_LEN));
+    NB_TRY(ctx->d_fp_window.alloc(sizeof(float2) * FP_HALF));
+    NB_TRY(ctx->d_fp_twiddle.alloc(sizeof(float2) * FP_HALF));
+    NB_TRY(ctx->d_fp_lane.alloc(sizeof(float2) * 32));
+    NB_TRY(ctx->d_fp_notes.alloc(sizeof(uint32_t) * 6 * 32));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_window.p, window.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_twiddle.p, tw.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_lane.p, lane_w.data(), sizeof(float2) * 32, cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_notes.p, notes.data(), sizeof(uint32_t) * 6 * 32, cudaMemcpyHostToDevice));
+    const int smem = (int)(sizeof(float2) * (2 * FP_HALF + FP_WARPS * XCHG_ELEMS));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ctx->fp_ready = true;
+    return NB200_OK;
+}
+
+int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
+                         uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out) {
+    if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;   // Rust's step_by(0) panics
+    if (ps->n_segments % 2 != 0) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    NB_TRY(ensure_fp_tables(ctx));
+
+    const uint32_t nseg = ps->n_segments;
+    std::vector<FpSegment> segs(nseg);
+    std::vector<uint64_t> seg_offset(nseg + 1, 0);
+    uint64_t frames = 0, tiles = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+        FpSegment &g = segs[s];
+        const uint64_t nf = num_frames(ps->n_mono[s]);
+        const uint64_t nr = num_raw(ps->n_mono[s]);
+        g.pcm_off = ps->dev_offset[s];
+        g.frame_begin = (uint32_t)frames;
+        g.n_frames = (uint32_t)nf;
+        g.n_raw = (uint32_t)nr;
+        g.tile_begin = (uint32_t)tiles;
+        g.pad = 0;
+        g.seek_to_ns = seek_to_ns ? seek_to_ns[s] : 0;
+        frames += nf;
+        tiles += (nr + K2_TILE - 1) / K2_TILE;
+        if (frames > 0x7fffffffull || tiles > 0x7fffffffull) return NB200_ERR_TOO_LARGE;
+        seg_offset[s + 1] = seg_offset[s] + (nr + stride - 1) / stride;
+    }
+
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    auto fail = [&](int st) {
+        delete hs;
+        return st;
+    };
+    {
+        // same aligned layout as nb200_hashset_upload
+        hs->n_videos = nseg / 2;
+        hs->seg_offset = seg_offset;
+        hs->dev_offset.resize(nseg);
+        hs->seg_len.resize(nseg);
+        uint64_t dev = 0;
+        for (uint32_t s = 0; s < nseg; s++) {
+            const uint64_t len = seg_offset[s + 1] - seg_offset[s];
+            hs->dev_offset[s] = (uint32_t)dev;
+            hs->seg_len[s] = (uint32_t)len;
+            segs[s].out_off = (uint32_t)dev;
+            dev += (len + 3) & ~3ull;
+            if (dev > 0xfffffff0ull) return fail(NB200_ERR_TOO_LARGE);
+        }
+        hs->total = seg_offset[nseg];
+        hs->dev_total = dev;
+        hs->ts_on_host = false;
+        hs->ts_formula = true;
+        hs->delay_ns = delay_ns;
+        hs->item_ns = item_ns;
+        hs->stride = stride;
+    }
+    if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t)) != NB200_OK ||
+        hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t)) != NB200_OK)
+        return fail(NB200_ERR_CUDA);
+    cudaStream_t st = ctx->stream;
+#define NB_CUDA_F(expr)                      \
+    do {                                     \
+        cudaError_t _e = (expr);             \
+        if (_e != cudaSuccess) {             \
+            set_last_error(#expr, _e);       \
+            return fail(NB200_ERR_CUDA);     \
+        }                                    \
+    } while (0)
+    ctx->ev_valid[0] = ctx->ev_valid[1] = false;
+    if (hs->dev_total > 0) {
+        NB_CUDA_F(cudaMemsetAsync(hs->d_hashes.p, 0, hs->dev_total * sizeof(uint32_t), st));
+        NB_CUDA_F(cudaMemsetAsync(hs->d_ts.p, 0, hs->dev_total * sizeof(uint64_t), st));
+    }
+    if (frames > 0) {
+        const size_t b_seg = (size_t)nseg * sizeof(FpSegment);
+        if (ctx->d_fp_desc.reserve(b_seg) != NB200_OK || ctx->h_stage.reserve(b_seg) != NB200_OK ||
+            ctx->d_chroma.reserve((size_t)(frames + 8) * FP_BANDS * sizeof(float)) != NB200_OK)
+            return fail(NB200_ERR_CUDA);
+        memcpy(ctx->h_stage.p, segs.data(), b_seg);
+        NB_CUDA_F(cudaMemcpyAsync(ctx->d_fp_desc.p, ctx->h_stage.p, b_seg, cudaMemcpyHostToDevice, st));
+
+        K1Args k1;
+        k1.pcm = ps->d_pcm.as<int16_t>();
+        k1.segs = ctx->d_fp_desc.as<FpSegment>();
+        k1.n_segs = nseg;
+        k1.total_frames = (uint32_t)frames;
+        k1.window = ctx->d_fp_window.as<float2>();
+        k1.twiddle = ctx->d_fp_twiddle.as<float2>();
+        k1.lane_w = ctx->d_fp_lane.as<float2>();
+        k1.notes = ctx->d_fp_notes.as<uint32_t>();
+        k1.chroma = ctx->d_chroma.as<float>();
+        const uint32_t n_blocks = (uint32_t)((frames + FP_WARPS - 1) / FP_WARPS);
+        const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, n_blocks);
+        const size_t smem = sizeof(float2) * (2 * FP_HALF + FP_WARPS * XCHG_ELEMS);
+        NB_CUDA_F(cudaEventRecord(ctx->ev[0], st));
+        fp_fft_chroma_kernel<<<grid1, FP_WARPS * 32, smem, st>>>(k1);
+        NB_CUDA_F(cudaGetLastError());
+        NB_CUDA_F(cudaEventRecord(ctx->ev[1], st));
+        ctx->ev_valid[0] = true;
+        ctx->n_launches++;
+
+        if (tiles > 0) {
+            K2Args k2;
+            k2.chroma = ctx->d_chroma.as<float>();
+            k2.segs = ctx->d_fp_desc.as<FpSegment>();
+            k2.n_segs = nseg;
+            k2.n_tiles = (uint32_t)tiles;
+            k2.stride = stride;
+            k2.item_secs = as_secs_f32(item_ns);
+            k2.delay_ns = delay_ns;
+            k2.out_hash = hs->d_hashes.as<uint32_t>();
+            k2.out_ts = hs->d_ts.as<uint64_t>();
+            NB_CUDA_F(cudaEventRecord(ctx->ev[2], st));
+            fp_classify_kernel<<<(uint32_t)tiles, K2_TILE, 0, st>>>(k2);
+            NB_CUDA_F(cudaGetLastError());
+            NB_CUDA_F(cudaEventRecord(ctx->ev[3], st));
+            ctx->ev_valid[1] = true;
+            ctx->n_launches++;
+        }
+        // h_stage is reused by later calls
+        NB_CUDA_F(cudaStreamSynchronize(st));
+    }
+#undef NB_CUDA_F
+    *out = hs;
+    return NB200_OK;
+}
+
+}  // namespace nb200
+
+using namespace nb200;
+
+struct nb200_fp {
+    nb200_ctx *ctx = nullptr;
+    bool started = false, finished = false;
+    int channels = 0;
+    PinnedBuf buf;            // interleaved i16 as fed
+    size_t n_samples = 0;     // i16 values accumulated
+    std::vector<uint32_t> raw;
+};
+
+extern "C" {
+
+uint64_t nb200_num_raw_hashes(uint64_t n_mono_samples) { return num_raw(n_mono_samples); }
+
+int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                        int channels, uint32_t n_segments, nb200_pcmset **out) {
+    if (!ctx || !out || (n_segments && (!pcm || !n_samples_total))) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    if (channels != 1 && channels != 2) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    nb200_pcmset *ps = new (std::nothrow) nb200_pcmset();
+    if (!ps) return NB200_ERR_TOO_LARGE;
+    ps->n_segments = n_segments;
+    ps->n_mono.resize(n_segments);
+    ps->dev_offset.resize(n_segments);
+    uint64_t dev = 0, max_seg = 0;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        if (n_samples_total[s] % (uint64_t)channels != 0 || (n_samples_total[s] && !pcm[s])) {
+            delete ps;
+            return NB200_ERR_INVALID_ARGUMENT;
+        }
+        ps->n_mono[s] = n_samples_total[s] / (uint64_t)channels;
+        ps->dev_offset[s] = dev;
+        dev += (ps->n_mono[s] + 7) & ~7ull;
+        max_seg = std::max(max_seg, n_samples_total[s]);
+    }
+    ps->dev_total = dev;
+    auto fail = [&](int st, const char *what, cudaError_t e) {
+        if (what) set_last_error(what, e);
+        delete ps;
+        return st;
+    };
+    if (ps->d_pcm.alloc((size_t)(dev + 8) * sizeof(int16_t)) != NB200_OK) return fail(NB200_ERR_CUDA, nullptr, cudaSuccess);
+    cudaStream_t st = ctx->stream;
+    cudaError_t e;
+    if (channels == 2 && ctx->d_stereo.reserve((size_t)max_seg * sizeof(int16_t)) != NB200_OK)
+        return fail(NB200_ERR_CUDA, nullptr, cudaSuccess);
+    for (uint32_t s = 0; s < n_segments; s++) {
+        if (ps->n_mono[s] == 0) continue;
+        int16_t *dst = ps->d_pcm.as<int16_t>() + ps->dev_offset[s];
+        if (channels == 1) {
+            e = cudaMemcpyAsync(dst, pcm[s], ps->n_mono[s] * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return fail(NB200_ERR_CUDA, "cudaMemcpyAsync(pcm)", e);
+        } else {
+            e = cudaMemcpyAsync(ctx->d_stereo.p, pcm[s], n_samples_total[s] * sizeof(int16_t),
+                                cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return fail(NB200_ERR_CUDA, "cudaMemcpyAsync(stereo pcm)", e);
+            const uint64_t n = ps->n_mono[s];
+            downmix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->d_stereo.as<int16_t>(), dst, n);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return fail(NB200_ERR_CUDA, "downmix_kernel", e);
+            ctx->n_launches++;
+        }
+    }
+    e = cudaStreamSynchronize(st);   // the caller may reuse its buffers
+    if (e != cudaSuccess) return fail(NB200_ERR_CUDA, "cudaStreamSynchronize", e);
+    *out = ps;
+    return NB200_OK;
+}
+
+void nb200_pcmset_free(nb200_pcmset *ps) { delete ps; }
+
+int nb200_fingerprint_run(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
+                          uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out) {
+    if (!ctx || !ps || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    return fingerprint_run_impl(ctx, ps, stride, delay_ns, item_ns, seek_to_ns, out);
+}
+
+int nb200_fingerprint_batch(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                            int channels, uint32_t n_segments, uint32_t stride, uint32_t **out_hashes,
+                            uint64_t *out_counts) {
+    if (!ctx || !out_hashes || !out_counts) return NB200_ERR_NULL_ARGUMENT;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        out_hashes[s] = nullptr;
+        out_counts[s] = 0;
+    }
+    if (n_segments == 0) return NB200_OK;
+    // the staged pipeline works on (opening, ending) segment pairs: pad to even
+    std::vector<const int16_t *> p(pcm, pcm + n_segments);
+    std::vector<uint64_t> c(n_samples_total, n_samples_total + n_segments);
+    if (n_segments & 1) {
+        p.push_back(nullptr);
+        c.push_back(0);
+    }
+    nb200_pcmset *ps = nullptr;
+    NB_TRY(nb200_pcmset_upload(ctx, p.data(), c.data(), channels, (uint32_t)p.size(), &ps));
+    nb200_hashset *hs = nullptr;
+    int st = fingerprint_run_impl(ctx, ps, stride, 0, 0, nullptr, &hs);
+    nb200_pcmset_free(ps);
+    if (st != NB200_OK) return st;
+    std::vector<uint32_t> h(std::max<uint64_t>(hs->total, 1));
+    std::vector<uint64_t> t(std::max<uint64_t>(hs->total, 1));
+    st = nb200_hashset_download(ctx, hs, h.data(), t.data());
+    if (st == NB200_OK) {
+        for (uint32_t s = 0; s < n_segments; s++) {
+            const uint64_t n = hs->seg_len[s];
+            uint32_t *o = (uint32_t *)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
+            if (!o) {
+                st = NB200_ERR_TOO_LARGE;
+                break;
+            }
+            memcpy(o, h.data() + hs->seg_offset[s], n * sizeof(uint32_t));
+            out_hashes[s] = o;
+            out_counts[s] = n;
+        }
+        if (st != NB200_OK)
+            for (uint32_t s = 0; s < n_segments; s++) {
+                free(out_hashes[s]);
+                out_hashes[s] = nullptr;
+                out_counts[s] = 0;
+            }
+    }
+    nb200_hashset_free(hs);
+    return st;
+}
+
+/* ---------------------------------------------- chromaprint-shaped shim */
+
+int nb200_fp_new(nb200_ctx *ctx, nb200_fp **out) {
+    if (!ctx || !out) return NB200_ERR_NULL_ARGUMENT;
+    nb200_fp *fp = new (std::nothrow) nb200_fp();
+    if (!fp) return NB200_ERR_TOO_LARGE;
+    fp->ctx = ctx;
+    *out = fp;
+    return NB200_OK;
+}
+
+void nb200_fp_free(nb200_fp *fp) { delete fp; }
+
+int nb200_fp_sample_rate(const nb200_fp *) { return FP_SAMPLE_RATE; }
+
+int nb200_fp_start(nb200_fp *fp, int sample_rate, int channels) {
+    if (!fp) return NB200_ERR_NULL_ARGUMENT;
+    // needle resamples to the context's own rate before feeding (analyzer.rs:179-187);
+    // there is no resampler on this side of the boundary
+    if (sample_rate != FP_SAMPLE_RATE || (channels != 1 && channels != 2)) return NB200_ERR_INVALID_ARGUMENT;
+    fp->started = true;
+    fp->finished = false;
+    fp->channels = channels;
+    fp->n_samples = 0;
+    fp->raw.clear();
+    return NB200_OK;
+}
+
+int nb200_fp_feed(nb200_fp *fp, const int16_t *data, size_t n_samples_total) {
+    if (!fp || (n_samples_total && !data)) return NB200_ERR_NULL_ARGUMENT;
+    if (!fp->started || fp->finished) return NB200_ERR_STATE;
+    const size_t need = (fp->n_samples + n_samples_total) * sizeof(int16_t);
+    if (need > fp->buf.bytes) {
+        // grow the pinned buffer, keeping what was fed so far
+        PinnedBuf bigger;
+        NB_TRY(bigger.reserve(std::max<size_t>(need * 2, 1u << 20)));
+        if (fp->n_samples) memcpy(bigger.p, fp->buf.p, fp->n_samples * sizeof(int16_t));
+        std::swap(fp->buf.p, bigger.p);
+        std::swap(fp->buf.bytes, bigger.bytes);
+    }
+    memcpy(fp->buf.as<int16_t>() + fp->n_samples, data, n_samples_total * sizeof(int16_t));
+    fp->n_samples += n_samples_total;
+    return NB200_OK;
+}
+
+int nb200_fp_finish(nb200_fp *fp) {
+    if (!fp) return NB200_ERR_NULL_ARGUMENT;
+    if (!fp->started || fp->finished) return NB200_ERR_STATE;
+    // a trailing odd sample of a stereo stream cannot form a frame: dropped, as
+    // Chromaprint's AudioProcessor consumes whole frames only
+    const uint64_t usable = fp->n_samples - fp->n_samples % (size_t)fp->channels;
+    const int16_t *p = fp->buf.as<int16_t>();
+    uint32_t *out = nullptr;
+    uint64_t count = 0;
+    NB_TRY(nb200_fingerprint_batch(fp->ctx, &p, &usable, fp->channels, 1, 1, &out, &count));
+    fp->raw.assign(out, out + count);
+    free(out);
+    fp->finished = true;
+    return NB200_OK;
+}
+
+int nb200_fp_get_delay_ms(const nb200_fp *fp, int *out) {
+    if (!fp || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = NB200_DELAY_MS;
+    return NB200_OK;
+}
+
+int nb200_fp_get_item_duration_ms(const nb200_fp *fp, int *out) {
+    if (!fp || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = NB200_ITEM_DURATION_MS;
+    return NB200_OK;
+}
+
+int nb200_fp_get_raw(const nb200_fp *fp, const uint32_t **hashes, size_t *n) {
+    if (!fp || !hashes || !n) return NB200_ERR_NULL_ARGUMENT;
+    if (!fp->finished) return NB200_ERR_STATE;
+    *hashes = fp->raw.data();
+    *n = fp->raw.size();
+    return NB200_OK;
+}
+
+/* ------------------------------------------------ fused analyze + search */
+
+int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t *hash_duration_ns,
+                         const nb200_match_params *params, nb200_search_result *results);
+
+int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                         int channels, uint32_t n_videos, const uint64_t *seek_to_ns,
+                         uint64_t hash_duration_ns, const nb200_match_params *params,
+                         nb200_search_result *results) {
+    if (!ctx || !pcm || !n_samples_total || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_videos < 2) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;
+    // step_by = hash_duration.as_millis() / item_duration.as_millis()   (analyzer.rs:293-297)
+    const uint64_t stride = (hash_duration_ns / 1000000ull) / NB200_ITEM_DURATION_MS;
+    if (stride == 0 || stride > 0xffffffffull) return NB200_ERR_INVALID_ARGUMENT;
+    nb200_pcmset *ps = nullptr;
+    NB_TRY(nb200_pcmset_upload(ctx, pcm, n_samples_total, channels, 2 * n_videos, &ps));
+    nb200_hashset *hs = nullptr;
+    int st = fingerprint_run_impl(ctx, ps, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
+                                  NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs);
+    nb200_pcmset_free(ps);
+    if (st != NB200_OK) return st;
+    std::vector<uint64_t> hd(n_videos, hash_duration_ns);
+    st = nb200_search_hashset(ctx, hs, hd.data(), params, results);
+    nb200_hashset_free(hs);
+    return st;
+}
+
+}  // extern "C"

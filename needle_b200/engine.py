@@ -1,0 +1,325 @@
+"""Thin object layer over the C ABI: contexts, device-resident seasons, PCM
+sets and run sets.  Everything here forwards to libneedle_b200.so; numpy is
+only used to hold host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import MatchParams, RUN_DTYPE, SearchResultC, check, lib, ptr
+
+DELAY_NS = 2_600_000_000        # chromaprint get_delay(): 2600 ms
+ITEM_NS = 123_000_000           # chromaprint get_item_duration(): 123 ms
+HASH_DURATION_NS = 300_000_012  # Duration::from_secs_f32(0.3)  (DEFAULT_HASH_DURATION)
+
+
+def match_params(threshold: int = 10, include_endings: bool = False,
+                 min_opening_ns: int = 20_000_000_000, min_ending_ns: int = 20_000_000_000,
+                 time_padding_ns: int = 0) -> MatchParams:
+    return MatchParams(threshold, 1 if include_endings else 0, min_opening_ns, min_ending_ns,
+                       time_padding_ns)
+
+
+def _pairs_arg(pairs):
+    if pairs is None:
+        return None, None, 0
+    a = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+    return a, ptr(a), a.shape[0]
+
+
+def _results_list(res, n):
+    return [res[v].astuple() for v in range(n)]
+
+
+class Context:
+    """nb200_ctx: one CUDA stream + scratch on one device."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        check(lib().nb200_ctx_create(device, C.byref(self._h)), "nb200_ctx_create")
+
+    def close(self):
+        if self._h:
+            lib().nb200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib().nb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None),
+              "nb200_ctx_set_stream")
+
+    def synchronize(self):
+        check(lib().nb200_ctx_synchronize(self._h), "nb200_ctx_synchronize")
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 4)()
+        n = C.c_uint64(0)
+        check(lib().nb200_ctx_last_kernel_ms(self._h, ms, C.byref(n)), "nb200_ctx_last_kernel_ms")
+        return {"fp_fft_chroma": ms[0], "fp_classify": ms[1], "match": ms[2], "simhash": ms[3],
+                "n_launches": n.value}
+
+    # ---------------------------------------------------------- host-buffer calls
+
+    def match_pairs(self, hashes, ts_ns, seg_offset, params: MatchParams, pairs=None) -> np.ndarray:
+        """nb200_match_pairs: structured array of runs in the reference's push order."""
+        h = np.ascontiguousarray(hashes, dtype=np.uint32)
+        t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+        off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        n_videos = (off.size - 1) // 2
+        _keep, pp, npairs = _pairs_arg(pairs)
+        out = C.POINTER(_lib.Run)()
+        n = C.c_uint64(0)
+        check(lib().nb200_match_pairs(self._h, ptr(h), ptr(t), ptr(off), n_videos, pp, npairs,
+                                      C.byref(params), C.byref(out), C.byref(n)), "nb200_match_pairs")
+        try:
+            if n.value == 0:
+                return np.zeros(0, dtype=RUN_DTYPE)
+            buf = C.cast(out, C.POINTER(C.c_uint8 * (n.value * C.sizeof(_lib.Run)))).contents
+            return np.frombuffer(buf, dtype=RUN_DTYPE).copy()
+        finally:
+            lib().nb200_free(out)
+
+    def search(self, hashes, ts_ns, seg_offset, hash_duration_ns, params: MatchParams):
+        """nb200_search: per-video result tuples (present, has_opening, has_ending,
+        opening_start_ns, opening_end_ns, ending_start_ns, ending_end_ns)."""
+        h = np.ascontiguousarray(hashes, dtype=np.uint32)
+        t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+        off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
+        n_videos = (off.size - 1) // 2
+        res = (SearchResultC * max(n_videos, 1))()
+        check(lib().nb200_search(self._h, ptr(h), ptr(t), ptr(off), ptr(hd), n_videos, C.byref(params),
+                                 res), "nb200_search")
+        return _results_list(res, n_videos)
+
+    def fingerprint_batch(self, segments, channels: int = 1, stride: int = 1):
+        """nb200_fingerprint_batch: list of u32 arrays (raw sub-fingerprints, every stride-th)."""
+        segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]
+        n = len(segs)
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in segs])
+        cnt = np.asarray([s.size for s in segs], dtype=np.uint64)
+        outs = (C.c_void_p * max(n, 1))()
+        out_counts = np.zeros(max(n, 1), np.uint64)
+        check(lib().nb200_fingerprint_batch(self._h, ptrs, ptr(cnt), channels, n, stride, outs,
+                                            ptr(out_counts)), "nb200_fingerprint_batch")
+        res = []
+        for k in range(n):
+            c = int(out_counts[k])
+            if c:
+                a = np.ctypeslib.as_array(C.cast(outs[k], C.POINTER(C.c_uint32)), shape=(c,)).copy()
+            else:
+                a = np.zeros(0, np.uint32)
+            res.append(a)
+            lib().nb200_free(outs[k])
+        return res
+
+    def analyze_search(self, segments, channels, seek_to_ns, hash_duration_ns, params: MatchParams):
+        """nb200_analyze_search: segments = [opening_0, ending_0, opening_1, ...] PCM arrays."""
+        segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]
+        n = len(segs)
+        assert n % 2 == 0
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in segs])
+        cnt = np.asarray([s.size for s in segs], dtype=np.uint64)
+        seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        res = (SearchResultC * max(n // 2, 1))()
+        check(lib().nb200_analyze_search(self._h, ptrs, ptr(cnt), channels, n // 2, ptr(seek),
+                                         hash_duration_ns, C.byref(params), res), "nb200_analyze_search")
+        return _results_list(res, n // 2)
+
+
+def vote(ts_ns, seg_offset, hash_duration_ns, params: MatchParams, runs: np.ndarray, pairs=None):
+    """nb200_vote (host only): runs as returned by match_pairs / RunSet.download."""
+    t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+    off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+    hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
+    r = np.ascontiguousarray(runs, dtype=RUN_DTYPE)
+    n_videos = (off.size - 1) // 2
+    _keep, pp, npairs = _pairs_arg(pairs)
+    res = (SearchResultC * max(n_videos, 1))()
+    check(lib().nb200_vote(None, ptr(t), ptr(off), ptr(hd), n_videos, pp, npairs, C.byref(params),
+                           ptr(r), r.shape[0], res), "nb200_vote")
+    return _results_list(res, n_videos)
+
+
+class HashSet:
+    """nb200_hashset: a season of hashes + timestamps resident in HBM."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    @staticmethod
+    def upload(ctx: Context, hashes, ts_ns, seg_offset) -> "HashSet":
+        h = np.ascontiguousarray(hashes, dtype=np.uint32)
+        t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+        off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_hashset_upload(ctx.handle, ptr(h), ptr(t), ptr(off), (off.size - 1) // 2,
+                                         C.byref(out)), "nb200_hashset_upload")
+        return HashSet(ctx, out)
+
+    @staticmethod
+    def from_device(ctx: Context, d_hashes: int, d_ts_ns: int, seg_offset) -> "HashSet":
+        off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_hashset_from_device(ctx.handle, C.c_void_p(d_hashes), C.c_void_p(d_ts_ns),
+                                              ptr(off), (off.size - 1) // 2, C.byref(out)),
+              "nb200_hashset_from_device")
+        return HashSet(ctx, out)
+
+    def info(self):
+        n = C.c_uint32(0)
+        total = C.c_uint64(0)
+        check(lib().nb200_hashset_info(self._h, C.byref(n), C.byref(total), None), "nb200_hashset_info")
+        off = np.zeros(2 * n.value + 1, np.uint64)
+        check(lib().nb200_hashset_info(self._h, None, None, ptr(off)), "nb200_hashset_info")
+        return n.value, total.value, off
+
+    def download(self):
+        n, total, off = self.info()
+        h = np.zeros(total, np.uint32)
+        t = np.zeros(total, np.uint64)
+        check(lib().nb200_hashset_download(self.ctx.handle, self._h, ptr(h), ptr(t)),
+              "nb200_hashset_download")
+        return h, t, off
+
+    def export_packed(self, d_hashes: int, d_ts_ns: int):
+        check(lib().nb200_hashset_export_packed(self.ctx.handle, self._h, C.c_void_p(d_hashes),
+                                                C.c_void_p(d_ts_ns)), "nb200_hashset_export_packed")
+
+    def match(self, params: MatchParams, pairs=None) -> "RunSet":
+        _keep, pp, npairs = _pairs_arg(pairs)
+        out = C.c_void_p()
+        check(lib().nb200_match_run(self.ctx.handle, self._h, pp, npairs, C.byref(params), C.byref(out)),
+              "nb200_match_run")
+        return RunSet(self.ctx, out)
+
+    def search(self, hash_duration_ns, params: MatchParams):
+        n, _, _ = self.info()
+        hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
+        res = (SearchResultC * max(n, 1))()
+        check(lib().nb200_search_hashset(self.ctx.handle, self._h, ptr(hd), C.byref(params), res),
+              "nb200_search_hashset")
+        return _results_list(res, n)
+
+    def free(self):
+        if self._h:
+            lib().nb200_hashset_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class RunSet:
+    """nb200_runset: match output in HBM."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+
+    def count(self):
+        n = C.c_uint64(0)
+        cells = C.c_uint64(0)
+        check(lib().nb200_runset_count(self._h, C.byref(n), C.byref(cells)), "nb200_runset_count")
+        return n.value, cells.value
+
+    def download(self) -> np.ndarray:
+        n, _ = self.count()
+        out = np.zeros(n, dtype=RUN_DTYPE)
+        check(lib().nb200_runset_download(self.ctx.handle, self._h, ptr(out)), "nb200_runset_download")
+        return out
+
+    def free(self):
+        if self._h:
+            lib().nb200_runset_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PcmSet:
+    """nb200_pcmset: decoded PCM segments in HBM (2 per video: opening, ending)."""
+
+    def __init__(self, ctx: Context, handle, n_segments: int):
+        self.ctx = ctx
+        self._h = handle
+        self.n_segments = n_segments
+
+    @staticmethod
+    def upload(ctx: Context, segments, channels: int = 1) -> "PcmSet":
+        segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]
+        n = len(segs)
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in segs])
+        cnt = np.asarray([s.size for s in segs], dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_pcmset_upload(ctx.handle, ptrs, ptr(cnt), channels, n, C.byref(out)),
+              "nb200_pcmset_upload")
+        return PcmSet(ctx, out, n)
+
+    def fingerprint(self, stride: int = 2, delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS,
+                    seek_to_ns=None) -> HashSet:
+        seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_fingerprint_run(self.ctx.handle, self._h, stride, delay_ns, item_ns, ptr(seek),
+                                          C.byref(out)), "nb200_fingerprint_run")
+        return HashSet(self.ctx, out)
+
+    def free(self):
+        if self._h:
+            lib().nb200_pcmset_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+@dataclass
+class PinnedArray:
+    """cudaHostAlloc'd numpy array (nb200_host_alloc)."""
+    array: np.ndarray
+    _ptr: int
+
+    @staticmethod
+    def empty(n: int, dtype) -> "PinnedArray":
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        check(lib().nb200_host_alloc(C.byref(p), max(n, 1) * dt.itemsize), "nb200_host_alloc")
+        buf = (C.c_uint8 * (max(n, 1) * dt.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt)[:n]
+        return PinnedArray(arr, p.value)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            check(lib().nb200_host_free(C.c_void_p(self._ptr)), "nb200_host_free")
+            self._ptr = 0
