@@ -161,6 +161,21 @@ class GpuBackend:
         _h, t, off = season.download()
         return t, off
 
+    def alloc_exchange(self, plan: SeasonPlan):
+        t = self.torch
+        send = t.zeros(plan.block_bytes, dtype=t.uint8, device=self.device)
+        recv = t.zeros(plan.block_bytes * plan.world, dtype=t.uint8, device=self.device)
+        return send, recv
+
+    def gather_runs(self, dist, runs, group=None):
+        return gather_runs(dist, runs, self.device, self.torch, group)
+
+    def vote(self, ts, off, hash_duration_ns, params, runs, pairs):
+        return self.engine.vote(ts, off, hash_duration_ns, params, runs, pairs=pairs)
+
+    def release(self, obj):
+        obj.free()
+
 
 def gather_runs(dist, runs: np.ndarray, device, torch, group=None) -> list | None:
     """All ranks contribute a run list; rank 0 gets the list of arrays.  Two
@@ -188,3 +203,77 @@ def gather_runs(dist, runs: np.ndarray, device, torch, group=None) -> list | Non
         blk = host[r * cap * RUN_DTYPE.itemsize:(r * cap + int(counts[r])) * RUN_DTYPE.itemsize]
         out.append(np.frombuffer(blk.tobytes(), dtype=RUN_DTYPE).copy())
     return out
+
+
+class SeasonJob:
+    """`needle search --analyze` for a library of videos across the ranks of a
+    process group (or on one GPU when dist is None): the public multi-GPU call.
+
+    Every rank constructs it with the same global metadata (per-segment sample
+    counts, seeks, pair list); each rank passes only ITS segments' PCM to
+    run_host / upload.  Rank 0 receives the per-video results."""
+
+    def __init__(self, backend, dist, n_mono_per_segment, seek_to_ns, hash_duration_ns, params,
+                 pairs=None, stride: int = 2, group=None):
+        self.backend = backend
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist is not None else 1
+        self.rank = dist.get_rank(group) if dist is not None else 0
+        self.params = params
+        self.plan = SeasonPlan.build(n_mono_per_segment, self.world, stride)
+        n_videos = self.plan.n_videos
+        self.seek_to_ns = np.zeros(2 * n_videos, np.uint64) if seek_to_ns is None else \
+            np.asarray(seek_to_ns, dtype=np.uint64)
+        self.hash_duration_ns = np.asarray(hash_duration_ns, dtype=np.uint64)
+        self.pairs = pair_list(n_videos) if pairs is None else \
+            np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self.slices = shard_pairs(self.plan.seg_len, self.pairs, self.world, bool(params.include_endings))
+        self.local_segs = self.plan.local_segments(self.rank)
+        self.local_seek = self.seek_to_ns[self.local_segs] if self.local_segs else np.zeros(0, np.uint64)
+        self._send = self._recv = None
+
+    # which of the global segments this rank must be given
+    def local_segment_ids(self):
+        return list(self.local_segs)
+
+    def upload(self, local_segments):
+        assert len(local_segments) == len(self.local_segs)
+        return self.backend.upload_pcm(local_segments)
+
+    def _buffers(self):
+        if self._send is None:
+            self._send, self._recv = self.backend.alloc_exchange(self.plan)
+        return self._send, self._recv
+
+    def run_resident(self, pcmset):
+        """fingerprint -> all-gather -> match -> gather -> vote.  Returns the list of
+        per-video result tuples on rank 0, None elsewhere."""
+        b = self.backend
+        send, recv = self._buffers()
+        b.fingerprint_into(pcmset, self.plan, self.local_seek, send)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(recv, send, group=self.group)
+        else:
+            recv = send
+        season = b.season_from_gathered(recv, self.plan)
+        start, end = self.slices[self.rank]
+        runs = b.match(season, self.params, self.pairs[start:end])
+        if self.world > 1:
+            gathered = b.gather_runs(self.dist, runs, self.group)
+        else:
+            gathered = [runs]
+        results = None
+        if self.rank == 0:
+            all_runs = merge_runs(gathered, self.slices)
+            ts, off = b.season_timestamps(season)
+            results = b.vote(ts, off, self.hash_duration_ns, self.params, all_runs, self.pairs)
+        b.release(season)
+        return results
+
+    def run_host(self, local_segments):
+        ps = self.upload(local_segments)
+        try:
+            return self.run_resident(ps)
+        finally:
+            self.backend.release(ps)

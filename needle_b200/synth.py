@@ -101,27 +101,35 @@ class PcmEpisode:
     credits_at: float
 
 
-def make_pcm_season(n_episodes: int, minutes: float, season_seed: int = 1, intro_s: float = 90.0,
-                    credits_s: float = 90.0) -> list[PcmEpisode]:
+def season_themes(season_seed: int, intro_s: float = 90.0, credits_s: float = 90.0):
+    """The audio every episode of a season shares: (intro, credits) as float arrays."""
     srng = np.random.default_rng(season_seed)
-    intro = _chords(srng, intro_s)
-    credits = _chords(srng, credits_s)
+    return _chords(srng, intro_s), _chords(srng, credits_s)
+
+
+def make_pcm_episode(season_seed: int, e: int, minutes: float, intro: np.ndarray, credits: np.ndarray) -> PcmEpisode:
+    """Episode e of a season: its own low-passed noise with the season's intro
+    and credits spliced in at episode-specific offsets, +-1 LSB dither."""
     D = minutes * 60.0
     n = int(round(D * SAMPLE_RATE))
-    eps = []
-    for e in range(n_episodes):
-        rng = np.random.default_rng(1000 * season_seed + e)
-        x = _noise(rng, n)
-        intro_at = float(rng.uniform(10.0, min(120.0, max(11.0, 0.5 * D - intro_s - 5.0))))
-        hi = max(6.0, min(60.0, 0.25 * D - credits_s - 1.0))
-        credits_at = float(D - credits_s - rng.uniform(5.0, hi))
-        a = int(intro_at * SAMPLE_RATE)
-        x[a:a + intro.size] = intro[:max(0, min(intro.size, n - a))]
-        b = int(credits_at * SAMPLE_RATE)
-        x[b:b + credits.size] = credits[:max(0, min(credits.size, n - b))]
-        x = x * 32767.0 + rng.integers(-1, 2, n)     # per-episode +-1 LSB dither
-        eps.append(PcmEpisode(np.clip(np.rint(x), -32768, 32767).astype(np.int16), intro_at, credits_at))
-    return eps
+    intro_s, credits_s = intro.size / SAMPLE_RATE, credits.size / SAMPLE_RATE
+    rng = np.random.default_rng(1000 * season_seed + e)
+    x = _noise(rng, n)
+    intro_at = float(rng.uniform(10.0, min(120.0, max(11.0, 0.5 * D - intro_s - 5.0))))
+    hi = max(6.0, min(60.0, 0.25 * D - credits_s - 1.0))
+    credits_at = float(D - credits_s - rng.uniform(5.0, hi))
+    a = int(intro_at * SAMPLE_RATE)
+    x[a:a + intro.size] = intro[:max(0, min(intro.size, n - a))]
+    b = int(credits_at * SAMPLE_RATE)
+    x[b:b + credits.size] = credits[:max(0, min(credits.size, n - b))]
+    x = x * 32767.0 + rng.integers(-1, 2, n)     # per-episode +-1 LSB dither
+    return PcmEpisode(np.clip(np.rint(x), -32768, 32767).astype(np.int16), intro_at, credits_at)
+
+
+def make_pcm_season(n_episodes: int, minutes: float, season_seed: int = 1, intro_s: float = 90.0,
+                    credits_s: float = 90.0) -> list[PcmEpisode]:
+    intro, credits = season_themes(season_seed, intro_s, credits_s)
+    return [make_pcm_episode(season_seed, e, minutes, intro, credits) for e in range(n_episodes)]
 
 
 def split_segments(pcm: np.ndarray, opening_pct: float = 0.5, ending_pct: float = 0.25):
