@@ -284,12 +284,16 @@ def run_b200(args):
     pcmset = job.upload(local_segments)
     results = job.run_resident(pcmset)          # also the parity sanity numbers printed below
     # bytes that come back per step: this rank's runs + the timestamp mirror the vote needs
-    _hs = pcmset.fingerprint(stride=2, seek_to_ns=job.local_seek)
-    _n, _total, _ = _hs.info()
-    _hs.free()
-    _season = backend.season_from_gathered(job._recv if world > 1 else job._send, job.plan)
-    n_runs_local = backend.match(_season, params, my_pairs).shape[0]
-    _season.free()
+    if world == 1:
+        _hs = pcmset.fingerprint(stride=2, seek_to_ns=job.local_seek)
+        _rs = _hs.match(params)
+        n_runs_local = _rs.count()[0]
+        _rs.free()
+        _hs.free()
+    else:
+        _season = backend.season_from_gathered(job._buffers()[1], job.plan)   # filled by the run above
+        n_runs_local = backend.match(_season, params, my_pairs).shape[0]
+        _season.free()
     d2h_bytes = 24 * n_runs_local + 16 + (8 * int(sl.sum()) if rank == 0 else 0)
 
     # bring the clocks up before anything is timed (idle parts sit at 120 MHz)

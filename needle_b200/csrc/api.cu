@@ -242,8 +242,8 @@ int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t 
     // stage in the aligned layout (pad entries are zero and never read unmasked)
     const size_t b_h = (size_t)hs->dev_total * sizeof(uint32_t);
     const size_t b_t = (size_t)hs->dev_total * sizeof(uint64_t);
-    if (ctx->h_stage.reserve(b_h + b_t + 16) != NB200_OK || hs->d_hashes.alloc(b_h) != NB200_OK ||
-        hs->d_ts.alloc(b_t) != NB200_OK) {
+    if (ctx->h_stage.reserve(b_h + b_t + 16) != NB200_OK || hs->d_hashes.alloc(b_h, ctx->pool) != NB200_OK ||
+        hs->d_ts.alloc(b_t, ctx->pool) != NB200_OK) {
         delete hs;
         return NB200_ERR_CUDA;
     }
@@ -284,8 +284,8 @@ static int pack_or_unpack(nb200_ctx *ctx, const nb200_hashset *hs, bool to_packe
     // device copies of the two offset tables
     const uint32_t nseg = 2 * hs->n_videos;
     DevBuf d_off, d_dev;
-    NB_TRY(d_off.alloc((nseg + 1) * sizeof(uint64_t)));
-    NB_TRY(d_dev.alloc(std::max<uint32_t>(nseg, 1) * sizeof(uint32_t)));
+    NB_TRY(d_off.alloc((nseg + 1) * sizeof(uint64_t), ctx->pool));
+    NB_TRY(d_dev.alloc(std::max<uint32_t>(nseg, 1) * sizeof(uint32_t), ctx->pool));
     NB_CUDA(cudaMemcpyAsync(d_off.p, hs->seg_offset.data(), (nseg + 1) * sizeof(uint64_t),
                             cudaMemcpyHostToDevice, ctx->stream));
     NB_CUDA(cudaMemcpyAsync(d_dev.p, hs->dev_offset.data(), nseg * sizeof(uint32_t),
@@ -354,8 +354,8 @@ int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *
     if (!hs) return NB200_ERR_TOO_LARGE;
     int st = layout_hashset(hs, seg_offset, n_videos);
     if (st == NB200_OK && hs->total > 0 && (!d_hashes || !d_ts_ns)) st = NB200_ERR_NULL_ARGUMENT;
-    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t));
-    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t));
+    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool);
+    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool);
     if (st == NB200_OK && hs->dev_total > 0) {
         cudaError_t e = cudaMemsetAsync(hs->d_hashes.p, 0, hs->dev_total * sizeof(uint32_t), ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(hs->d_ts.p, 0, hs->dev_total * sizeof(uint64_t), ctx->stream);
@@ -388,11 +388,11 @@ int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, co
     if (!hs) return NB200_ERR_TOO_LARGE;
     int st = layout_hashset(hs, seg_offset.data(), n_videos);
     if (st == NB200_OK && hs->total > 0 && (!d_hashes || !d_ts_ns)) st = NB200_ERR_NULL_ARGUMENT;
-    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t));
-    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t));
+    if (st == NB200_OK) st = hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool);
+    if (st == NB200_OK) st = hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool);
     DevBuf d_tab;   // seg_offset | src_hash_off | src_ts_off | dev_offset
     const size_t b64 = (size_t)(nseg + 1) * sizeof(uint64_t);
-    if (st == NB200_OK) st = d_tab.alloc(3 * b64 + (size_t)std::max<uint32_t>(nseg, 1) * sizeof(uint32_t));
+    if (st == NB200_OK) st = d_tab.alloc(3 * b64 + (size_t)std::max<uint32_t>(nseg, 1) * sizeof(uint32_t), ctx->pool);
     if (st == NB200_OK && hs->total > 0) {
         cudaStream_t s = ctx->stream;
         char *tab = d_tab.as<char>();

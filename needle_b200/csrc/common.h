@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -30,15 +31,69 @@ void set_last_error_msg(const std::string &msg);
         if (_s != NB200_OK) return _s; \
     } while (0)
 
-// Simple RAII device buffer.
+// Per-context cache of device allocations: cudaMalloc/cudaFree cost tens of
+// microseconds each and cudaFree synchronises the device, which matters when a
+// whole step is a few milliseconds.  Blocks are handed back on release and
+// reused for requests of similar size.  Shared ownership: objects made by a
+// context may outlive it.
+struct DevPool {
+    struct Block {
+        void *p;
+        size_t bytes;
+    };
+    std::vector<Block> free_blocks;
+    size_t cached_bytes = 0;
+    void *get(size_t want, size_t *got) {
+        size_t best = free_blocks.size();
+        for (size_t k = 0; k < free_blocks.size(); k++)
+            if (free_blocks[k].bytes >= want && free_blocks[k].bytes <= 2 * want + (1u << 16) &&
+                (best == free_blocks.size() || free_blocks[k].bytes < free_blocks[best].bytes))
+                best = k;
+        if (best == free_blocks.size()) return nullptr;
+        Block b = free_blocks[best];
+        free_blocks.erase(free_blocks.begin() + (long)best);
+        cached_bytes -= b.bytes;
+        *got = b.bytes;
+        return b.p;
+    }
+    void put(void *p, size_t bytes) {
+        free_blocks.push_back({p, bytes});
+        cached_bytes += bytes;
+        // keep the cache bounded: drop the largest blocks beyond 8 GiB / 64 entries
+        while (free_blocks.size() > 64 || cached_bytes > (8ull << 30)) {
+            size_t big = 0;
+            for (size_t k = 1; k < free_blocks.size(); k++)
+                if (free_blocks[k].bytes > free_blocks[big].bytes) big = k;
+            cudaFree(free_blocks[big].p);
+            cached_bytes -= free_blocks[big].bytes;
+            free_blocks.erase(free_blocks.begin() + (long)big);
+        }
+    }
+    ~DevPool() {
+        for (auto &b : free_blocks) cudaFree(b.p);
+    }
+};
+
+// Simple RAII device buffer (optionally backed by a DevPool).
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
-    int alloc(size_t n) {
+    std::shared_ptr<DevPool> pool;
+    int alloc(size_t n, const std::shared_ptr<DevPool> &from = nullptr) {
         release();
         if (n == 0) n = 16;
+        if (from) {
+            size_t got = 0;
+            if (void *q = from->get(n, &got)) {
+                p = q;
+                bytes = got;
+                pool = from;
+                return NB200_OK;
+            }
+        }
         NB_CUDA(cudaMalloc(&p, n));
         bytes = n;
+        pool = from;
         return NB200_OK;
     }
     // Grow-only (amortised scratch).
@@ -47,9 +102,12 @@ struct DevBuf {
         return alloc(n + n / 4);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool) pool->put(p, bytes); else cudaFree(p);
+        }
         p = nullptr;
         bytes = 0;
+        pool.reset();
     }
     ~DevBuf() { release(); }
     DevBuf() = default;
@@ -90,6 +148,7 @@ struct nb200_ctx {
     cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
     bool ev_valid[4] = {false, false, false, false};
     uint64_t n_launches = 0;
+    std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_runs_sorted;
     nb200::PinnedBuf h_stage, h_small;

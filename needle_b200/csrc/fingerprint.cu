@@ -558,8 +558,8 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
         hs->item_ns = item_ns;
         hs->stride = stride;
     }
-    if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t)) != NB200_OK ||
-        hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t)) != NB200_OK)
+    if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
+        hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK)
         return fail(NB200_ERR_CUDA);
     cudaStream_t st = ctx->stream;
 #define NB_CUDA_F(expr)                      \
@@ -674,7 +674,7 @@ int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_
         delete ps;
         return st;
     };
-    if (ps->d_pcm.alloc((size_t)(dev + 8) * sizeof(int16_t)) != NB200_OK) return fail(NB200_ERR_CUDA, nullptr, cudaSuccess);
+    if (ps->d_pcm.alloc((size_t)(dev + 8) * sizeof(int16_t), ctx->pool) != NB200_OK) return fail(NB200_ERR_CUDA, nullptr, cudaSuccess);
     cudaStream_t st = ctx->stream;
     cudaError_t e;
     if (channels == 2 && ctx->d_stereo.reserve((size_t)max_seg * sizeof(int16_t)) != NB200_OK)

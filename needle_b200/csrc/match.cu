@@ -534,7 +534,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         NB_CUDA_F(cudaEventRecord(ctx->ev[7], s));
         ctx->ev_valid[3] = true;
         ctx->n_launches++;
-        if (rs->d_runs.alloc((size_t)nr * sizeof(DeviceRun)) != NB200_OK) return fail(NB200_ERR_CUDA);
+        if (rs->d_runs.alloc((size_t)nr * sizeof(DeviceRun), ctx->pool) != NB200_OK) return fail(NB200_ERR_CUDA);
         NB_CUDA_F(cudaMemcpyAsync(rs->d_runs.p, ctx->d_runs.p, (size_t)nr * sizeof(DeviceRun),
                                   cudaMemcpyDeviceToDevice, s));
     }

@@ -145,6 +145,14 @@ class GpuBackend:
         hs.export_packed(send.data_ptr(), send.data_ptr() + 4 * plan.cap)
         hs.free()
 
+    def fingerprint_search(self, pcmset, plan: SeasonPlan, seek_to_ns, hash_duration_ns, params):
+        """Single-GPU path: nb200_fingerprint_run + nb200_search_hashset."""
+        hs = pcmset.fingerprint(stride=plan.stride, seek_to_ns=seek_to_ns)
+        try:
+            return hs.search(hash_duration_ns, params)
+        finally:
+            hs.free()
+
     def season_from_gathered(self, recv, plan: SeasonPlan):
         return self.engine.HashSet.from_device_scattered(self.ctx, recv.data_ptr(), recv.data_ptr(),
                                                          plan.src_hash_off, plan.src_ts_off, plan.seg_len)
@@ -228,6 +236,7 @@ class SeasonJob:
         self.hash_duration_ns = np.asarray(hash_duration_ns, dtype=np.uint64)
         self.pairs = pair_list(n_videos) if pairs is None else \
             np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self._all_pairs = np.array_equal(self.pairs, pair_list(n_videos))
         self.slices = shard_pairs(self.plan.seg_len, self.pairs, self.world, bool(params.include_endings))
         self.local_segs = self.plan.local_segments(self.rank)
         self.local_seek = self.seek_to_ns[self.local_segs] if self.local_segs else np.zeros(0, np.uint64)
@@ -250,6 +259,9 @@ class SeasonJob:
         """fingerprint -> all-gather -> match -> gather -> vote.  Returns the list of
         per-video result tuples on rank 0, None elsewhere."""
         b = self.backend
+        if self.world == 1 and self._all_pairs and hasattr(b, "fingerprint_search"):
+            # one GPU, default pair list: no exchange buffers, two C-ABI calls
+            return b.fingerprint_search(pcmset, self.plan, self.local_seek, self.hash_duration_ns, self.params)
         send, recv = self._buffers()
         b.fingerprint_into(pcmset, self.plan, self.local_seek, send)
         if self.world > 1:
