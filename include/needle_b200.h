@@ -74,6 +74,12 @@ int nb200_ctx_synchronize(nb200_ctx *ctx);
  * in n_launches (may be NULL). */
 int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
 
+/* Tuning / test switches.  NB200_OPT_FORCE_GENERAL_MATCH (value 0|1): always run
+ * the general match kernel, also where the fast variant (all candidate run
+ * lengths >= 63 cells) would be chosen.  Results are identical either way. */
+enum { NB200_OPT_FORCE_GENERAL_MATCH = 1 };
+int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
+
 /* Pinned host memory (cudaHostAlloc) for PCM / hash staging. */
 int nb200_host_alloc(void **out, size_t bytes);
 int nb200_host_free(void *p);

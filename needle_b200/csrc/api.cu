@@ -180,6 +180,17 @@ int nb200_ctx_set_stream(nb200_ctx *ctx, void *cuda_stream) {
     return NB200_OK;
 }
 
+int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
+    if (!ctx) return NB200_ERR_NULL_ARGUMENT;
+    switch (option) {
+    case NB200_OPT_FORCE_GENERAL_MATCH:
+        ctx->force_general_match = value != 0;
+        return NB200_OK;
+    default:
+        return NB200_ERR_INVALID_ARGUMENT;
+    }
+}
+
 int nb200_ctx_synchronize(nb200_ctx *ctx) {
     if (!ctx) return NB200_ERR_NULL_ARGUMENT;
     NB_CUDA(cudaStreamSynchronize(ctx->stream));

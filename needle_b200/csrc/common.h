@@ -148,6 +148,7 @@ struct nb200_ctx {
     cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
     bool ev_valid[4] = {false, false, false, false};
     uint64_t n_launches = 0;
+    bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_runs_sorted;

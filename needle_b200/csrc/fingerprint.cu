@@ -46,6 +46,8 @@ constexpr int K2_COLS = FP_BANDS + 1;
 __constant__ float2 c_w64[64];    // exp(-2 pi i e / 64)
 __constant__ float2 c_w32[32];    // exp(-2 pi i e / 32)
 __constant__ float2 c_w128[FP_T]; // exp(-2 pi i t / 128) = W_4096^(32 t)
+// the same twiddles as (-w.y, w.x): second operand of the packed complex multiply
+__constant__ float2 c_w64r[64], c_w32r[32], c_w128r[FP_T];
 
 struct K2Classifier {
     int type, y, h, w;
@@ -62,72 +64,87 @@ static uint64_t num_raw(uint64_t n_mono) {
     return f > (uint64_t)FP_WARMUP ? f - FP_WARMUP : 0;
 }
 
-// ------------------------------------------------------------ complex helpers
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
-    return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
-}
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // * (-i)
+// ------------------------------------------------- packed complex arithmetic
+// A complex number is one float2 = one aligned register pair; sm_100a has packed
+// FP32x2 instructions (FADD2 / FMUL2 / FFMA2) with broadcast and swap operand
+// modifiers, so a complex add is ONE instruction and a complex multiply two or
+// three.  Half the issue slots of scalar code for the same flops.
+using f2 = float2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 bx(f2 a) { return make_float2(a.x, a.x); }
+__device__ __forceinline__ f2 by(f2 a) { return make_float2(a.y, a.y); }
+__device__ __forceinline__ f2 swp(f2 a) { return make_float2(a.y, a.x); }
+// a * w for a run-time w
+__device__ __forceinline__ f2 cmul(f2 a, f2 w) { return fma2(by(a), make_float2(-w.y, w.x), mul2(bx(a), w)); }
+// a * w with wr = (-w.y, w.x) supplied (tables of constants carry both forms)
+__device__ __forceinline__ f2 cmulc(f2 a, f2 w, f2 wr) { return fma2(by(a), wr, mul2(bx(a), w)); }
+// d + (-i) t   and   d - (-i) t
+__device__ __forceinline__ f2 add_mi(f2 d, f2 t) { return fma2(swp(t), make_float2(1.f, -1.f), d); }
+__device__ __forceinline__ f2 sub_mi(f2 d, f2 t) { return fma2(swp(t), make_float2(-1.f, 1.f), d); }
 
 // Forward DFTs on register arrays; S = element stride.  Natural order in and out.
-template <int S> __device__ __forceinline__ void fft4(float2 *v) {
-    const float2 c0 = v[0], c1 = v[S], c2 = v[2 * S], c3 = v[3 * S];
-    const float2 d0 = cadd(c0, c2), d1 = csub(c0, c2), d2 = cadd(c1, c3), d3 = mul_mi(csub(c1, c3));
-    v[0] = cadd(d0, d2);
-    v[S] = cadd(d1, d3);
-    v[2 * S] = csub(d0, d2);
-    v[3 * S] = csub(d1, d3);
+template <int S> __device__ __forceinline__ void fft4(f2 *v) {
+    const f2 c0 = v[0], c1 = v[S], c2 = v[2 * S], c3 = v[3 * S];
+    const f2 d0 = add2(c0, c2), d1 = sub2(c0, c2), d2 = add2(c1, c3), e = sub2(c1, c3);
+    v[0] = add2(d0, d2);
+    v[S] = add_mi(d1, e);
+    v[2 * S] = sub2(d0, d2);
+    v[3 * S] = sub_mi(d1, e);
 }
 
-template <int S> __device__ __forceinline__ void fft8(float2 *v) {
+template <int S> __device__ __forceinline__ void fft8(f2 *v) {
     constexpr float R = 0.70710678118654752440f;
-    const float2 a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S];
-    const float2 a4 = v[4 * S], a5 = v[5 * S], a6 = v[6 * S], a7 = v[7 * S];
+    const f2 a0 = v[0], a1 = v[S], a2 = v[2 * S], a3 = v[3 * S];
+    const f2 a4 = v[4 * S], a5 = v[5 * S], a6 = v[6 * S], a7 = v[7 * S];
     // X[2r] = FFT4(a_j + a_{j+4}),  X[2r+1] = FFT4((a_j - a_{j+4}) W8^j)
-    const float2 b0 = cadd(a0, a4), b1 = cadd(a1, a5), b2 = cadd(a2, a6), b3 = cadd(a3, a7);
-    const float2 b4 = csub(a0, a4);
-    const float2 t5 = csub(a1, a5), t7 = csub(a3, a7);
-    const float2 b5 = make_float2((t5.x + t5.y) * R, (t5.y - t5.x) * R);     // * (1 - i)/sqrt2
-    const float2 b6 = mul_mi(csub(a2, a6));
-    const float2 b7 = make_float2((t7.y - t7.x) * R, -(t7.x + t7.y) * R);    // * (-1 - i)/sqrt2
+    const f2 b0 = add2(a0, a4), b1 = add2(a1, a5), b2 = add2(a2, a6), b3 = add2(a3, a7);
+    const f2 b4 = sub2(a0, a4), t5 = sub2(a1, a5), e6 = sub2(a2, a6), t7 = sub2(a3, a7);
+    // t5 (1-i)/sqrt2 = t5.x (R,-R) + t5.y (R,R);   t7 (-1-i)/sqrt2 = t7.x (-R,-R) + t7.y (R,-R)
+    const f2 b5 = fma2(by(t5), make_float2(R, R), mul2(bx(t5), make_float2(R, -R)));
+    const f2 b7 = fma2(by(t7), make_float2(R, -R), mul2(bx(t7), make_float2(-R, -R)));
     {
-        const float2 d0 = cadd(b0, b2), d1 = csub(b0, b2), d2 = cadd(b1, b3), d3 = mul_mi(csub(b1, b3));
-        v[0] = cadd(d0, d2);
-        v[2 * S] = cadd(d1, d3);
-        v[4 * S] = csub(d0, d2);
-        v[6 * S] = csub(d1, d3);
+        const f2 d0 = add2(b0, b2), d1 = sub2(b0, b2), d2 = add2(b1, b3), e = sub2(b1, b3);
+        v[0] = add2(d0, d2);
+        v[2 * S] = add_mi(d1, e);
+        v[4 * S] = sub2(d0, d2);
+        v[6 * S] = sub_mi(d1, e);
     }
     {
-        const float2 d0 = cadd(b4, b6), d1 = csub(b4, b6), d2 = cadd(b5, b7), d3 = mul_mi(csub(b5, b7));
-        v[S] = cadd(d0, d2);
-        v[3 * S] = cadd(d1, d3);
-        v[5 * S] = csub(d0, d2);
-        v[7 * S] = csub(d1, d3);
+        // b6 = (-i) e6 is folded into the butterflies
+        const f2 d0 = add_mi(b4, e6), d1 = sub_mi(b4, e6), d2 = add2(b5, b7), e = sub2(b5, b7);
+        v[S] = add2(d0, d2);
+        v[3 * S] = add_mi(d1, e);
+        v[5 * S] = sub2(d0, d2);
+        v[7 * S] = sub_mi(d1, e);
     }
 }
 
 // 64-point FFT, n = n1 + 8 n2, k = 8 k1 + k2: X[8 k1 + k2] ends up at v[k1 + 8 k2].
-__device__ __forceinline__ void fft64(float2 *v) {
+__device__ __forceinline__ void fft64(f2 *v) {
 #pragma unroll
     for (int n1 = 0; n1 < 8; n1++) fft8<8>(v + n1);
 #pragma unroll
     for (int n1 = 1; n1 < 8; n1++)
 #pragma unroll
-        for (int k2 = 1; k2 < 8; k2++) v[n1 + 8 * k2] = cmul(v[n1 + 8 * k2], c_w64[n1 * k2]);
+        for (int k2 = 1; k2 < 8; k2++)
+            v[n1 + 8 * k2] = cmulc(v[n1 + 8 * k2], c_w64[n1 * k2], c_w64r[n1 * k2]);
 #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) fft8<1>(v + 8 * k2);
 }
 __device__ __forceinline__ constexpr int pos64(int k) { return (k >> 3) + 8 * (k & 7); }
 
 // 32-point FFT, n = n1 + 8 n2 (n2 < 4), k = 4 k1 + k2: X[4 k1 + k2] at v[k1 + 8 k2].
-__device__ __forceinline__ void fft32(float2 *v) {
+__device__ __forceinline__ void fft32(f2 *v) {
 #pragma unroll
     for (int n1 = 0; n1 < 8; n1++) fft4<8>(v + n1);
 #pragma unroll
     for (int n1 = 1; n1 < 8; n1++)
 #pragma unroll
-        for (int k2 = 1; k2 < 4; k2++) v[n1 + 8 * k2] = cmul(v[n1 + 8 * k2], c_w32[n1 * k2]);
+        for (int k2 = 1; k2 < 4; k2++)
+            v[n1 + 8 * k2] = cmulc(v[n1 + 8 * k2], c_w32[n1 * k2], c_w32r[n1 * k2]);
 #pragma unroll
     for (int k2 = 0; k2 < 4; k2++) fft8<1>(v + 8 * k2);
 }
@@ -136,12 +153,37 @@ __device__ __forceinline__ constexpr int pos32(int k) { return (k >> 2) + 8 * (k
 __device__ __forceinline__ constexpr int zslot(int t) { return (t & 1) * 32 + pos32(t >> 1); }
 
 // two packed i16 -> two floats without I2F: 0x4B00hhhh is 2^23 + hhhh
-__device__ __forceinline__ float2 s16x2_to_float(uint32_t w) {
+__device__ __forceinline__ f2 s16x2_to_float(uint32_t w) {
     w ^= 0x80008000u;   // bias to unsigned
-    const float lo = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8421376.0f;
-    const float hi = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8421376.0f;
-    return make_float2(lo, hi);
+    const f2 biased = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)),
+                                  __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)));
+    return add2(biased, make_float2(-8421376.0f, -8421376.0f));
 }
+
+// ---- 1-D bulk async copy (TMA) + mbarrier, shared::cta addresses as u32
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NB_DONE_%=;\n"
+        "bra NB_WAIT_%=;\n"
+        "NB_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct FpSegment {
     uint64_t pcm_off;      // element offset of the segment's mono PCM
@@ -162,15 +204,30 @@ struct K1Args {
     const float2 *window;    // [2048]  (w[2n], w[2n+1]) / 32767
     const float2 *twiddle;   // [32][64] W_2048^(n2 k1)
     const float2 *lane_w;    // [32] W_4096^L
-    const uint32_t *notes;   // [6][32] 4-bit pitch class of bin L + 32 t (12 = unused)
     float *chroma;           // [total_frames][12]
 };
 
+constexpr int PCM_COPY_BYTES = FP_FRAME * 2 + 16;   // the frame plus alignment slack, multiple of 16
+constexpr int K1_WARP_BYTES = XCHG_ELEMS * 8;       // 16,896 B: transpose buffer, doubles as PCM landing zone
+static_assert(PCM_COPY_BYTES <= K1_WARP_BYTES, "PCM must fit the exchange buffer");
+constexpr int K1_SMEM_BYTES = 2 * FP_HALF * 8 + FP_WARPS * K1_WARP_BYTES + FP_WARPS * 8;
+
+// address of frame `frame`'s first sample (binary search over the segment table)
+__device__ __forceinline__ const int16_t *frame_src(const K1Args &a, uint32_t frame) {
+    uint32_t lo = 0, hi = a.n_segs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.segs[mid].frame_begin <= frame) lo = mid; else hi = mid;
+    }
+    return a.pcm + a.segs[lo].pcm_off + (uint64_t)(frame - a.segs[lo].frame_begin) * FP_HOP;
+}
+
 __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K1Args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_window = reinterpret_cast<float2 *>(smem_raw);           // 2048
-    float2 *s_twiddle = s_window + FP_HALF;                            // 2048
-    float2 *s_xchg_all = s_twiddle + FP_HALF;                          // FP_WARPS * XCHG_ELEMS
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    f2 *s_window = reinterpret_cast<f2 *>(smem_raw);                     // 2048
+    f2 *s_twiddle = s_window + FP_HALF;                                  // 2048
+    unsigned char *s_warp = reinterpret_cast<unsigned char *>(s_twiddle + FP_HALF);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_warp + FP_WARPS * K1_WARP_BYTES);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -178,55 +235,57 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
         s_window[i] = a.window[i];
         s_twiddle[i] = a.twiddle[i];
     }
+    if (threadIdx.x < FP_WARPS) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    float2 *xchg = s_xchg_all + warp * XCHG_ELEMS;
-    float *acc = reinterpret_cast<float *>(xchg);     // [13][32], reused after pass 2
+    f2 *xchg = reinterpret_cast<f2 *>(s_warp + warp * K1_WARP_BYTES);
+    const uint32_t *pcm_words = reinterpret_cast<const uint32_t *>(xchg);
+    const uint32_t bar = smem_u32(s_bar + warp);
+    const uint32_t xchg_addr = smem_u32(xchg);
     const int partner = (32 - lane) & 31;
-    const float2 lane_w = a.lane_w[lane];
-    uint32_t notes[6];
-#pragma unroll
-    for (int q = 0; q < 6; q++) notes[q] = a.notes[q * 32 + lane];
+    const f2 lane_w = a.lane_w[lane];
 
     const uint32_t n_blocks = (a.total_frames + FP_WARPS - 1) / FP_WARPS;
-    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const uint32_t frame = blk * FP_WARPS + warp;
-        if (frame >= a.total_frames) continue;   // warp-uniform; no block barrier below
-        // segment of this frame: last s with frame_begin <= frame
-        uint32_t lo = 0, hi = a.n_segs;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (a.segs[mid].frame_begin <= frame) lo = mid; else hi = mid;
+    uint32_t blk = blockIdx.x;
+    uint32_t frame = blk * FP_WARPS + warp;
+    uint32_t phase = 0;
+    // misalignment (bytes, even, < 16) of the frame that is in flight / resident
+    uint32_t delta = 0;
+    if (blk < n_blocks && frame < a.total_frames) {
+        const int16_t *src = frame_src(a, frame);
+        delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        if (lane == 0) {
+            mbar_expect_tx(bar, PCM_COPY_BYTES);
+            bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
         }
-        const FpSegment sg = a.segs[lo];
-        const int16_t *src = a.pcm + sg.pcm_off + (uint64_t)(frame - sg.frame_begin) * FP_HOP;
+    }
 
-        float2 v[64];
-        // ---- load + window: z[32 m + L] = (x[2n] w[2n], x[2n+1] w[2n+1])
-        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + lane;
+    for (; blk < n_blocks; blk += gridDim.x) {
+        frame = blk * FP_WARPS + warp;
+        if (frame >= a.total_frames) break;   // warp-uniform; only warp-level sync below
+
+        f2 v[64];
+        // ---- PCM (landed by the bulk copy) -> registers, window fused:
+        //      z[32 m + L] = (x[2n] w[2n], x[2n+1] w[2n+1])
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        {
+            const uint32_t *p = pcm_words + (delta >> 2) + lane;
+            const uint32_t shift = (delta & 2) * 8;
 #pragma unroll
             for (int m = 0; m < 64; m++) {
-                const float2 s = s16x2_to_float(__ldg(p + 32 * m));
-                const float2 w = s_window[32 * m + lane];
-                v[m] = make_float2(s.x * w.x, s.y * w.y);
-            }
-        } else {
-            const uint16_t *p = reinterpret_cast<const uint16_t *>(src) + 2 * lane;
-#pragma unroll
-            for (int m = 0; m < 64; m++) {
-                const uint32_t wlo = __ldg(p + 64 * m), whi = __ldg(p + 64 * m + 1);
-                const float2 s = s16x2_to_float(wlo | (whi << 16));
-                const float2 w = s_window[32 * m + lane];
-                v[m] = make_float2(s.x * w.x, s.y * w.y);
+                const uint32_t w0 = p[32 * m], w1 = p[32 * m + 1];
+                const f2 s = s16x2_to_float(__funnelshift_r(w0, w1, shift));
+                v[m] = mul2(s, s_window[32 * m + lane]);
             }
         }
+        __syncwarp();
 
         // ---- pass 1: 64-point FFT over m; Y[k1] (for n2 = L) at v[pos64(k1)]
         fft64(v);
 
         // ---- transpose: S[k1][n2]
-        __syncwarp();
 #pragma unroll
         for (int k1 = 0; k1 < 64; k1++) xchg[k1 * XCHG_STRIDE + lane] = v[pos64(k1)];
         __syncwarp();
@@ -238,50 +297,63 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
                 v[q * 32 + n2] = cmul(xchg[(lane + 32 * q) * XCHG_STRIDE + n2],
                                       s_twiddle[n2 * 64 + lane + 32 * q]);
         __syncwarp();
+        // ---- the exchange buffer is free: start the next frame's PCM on its way
+        {
+            const uint32_t nblk = blk + gridDim.x;
+            const uint32_t nframe = nblk * FP_WARPS + warp;
+            if (nblk < n_blocks && nframe < a.total_frames) {
+                const int16_t *src = frame_src(a, nframe);
+                delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+                fence_proxy_async();   // our generic reads of xchg are ordered before the async write
+                if (lane == 0) {
+                    mbar_expect_tx(bar, PCM_COPY_BYTES);
+                    bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+                }
+            }
+        }
         fft32(v);
         fft32(v + 32);
         // now Z[L + 32 t] = v[zslot(t)]
 
-        // ---- split + power + chroma fold
+        // ---- split + power + chroma fold (pitch classes are compile-time lane ranges)
+        float acc[FP_BANDS];
 #pragma unroll
-        for (int r = 0; r < 13; r++) acc[r * 32 + lane] = 0.f;
+        for (int b = 0; b < FP_BANDS; b++) acc[b] = 0.f;
 #pragma unroll
         for (int t = 0; t < FP_T; t++) {
-            const float2 z = v[zslot(t)];
-            const float2 ps = v[zslot(63 - t)];
-            float2 zp;
+            const f2 z = v[zslot(t)];
+            const f2 ps = v[zslot(63 - t)];
+            f2 zp;
             zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
             zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
             if (t >= 1) {   // lane 0 pairs k = 32 t with 2048 - 32 t, which it holds itself
-                const float2 own = v[zslot(t >= 1 ? 64 - t : 0)];
+                const f2 own = v[zslot(t >= 1 ? 64 - t : 0)];
                 if (lane == 0) zp = own;
             }
-            // 2E = (a+c, b-d), 2O = (b+d, -(a-c)) with Z[k] = a+ib, Z[N-k] = c+id
-            const float er = z.x + zp.x, ei = z.y - zp.y;
-            const float orr = z.y + zp.y, oi = zp.x - z.x;
-            const float2 w = cmul(lane_w, c_w128[t]);            // W_4096^(L + 32 t)
-            const float xr = er + (orr * w.x - oi * w.y);
-            const float xi = ei + (orr * w.y + oi * w.x);
-            const float pw = 0.25f * (xr * xr + xi * xi);
-            const uint32_t note = (notes[t >> 3] >> (4 * (t & 7))) & 15u;
-            acc[note * 32 + lane] += pw;
+            // 2E = (a+c, b-d), 2O = (b+d, c-a) with Z[k] = a+ib, Z[N-k] = c+id
+            const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+            const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+            const f2 w = cmulc(lane_w, c_w128[t], c_w128r[t]);            // W_4096^(L + 32 t)
+            const f2 x = add2(e, cmul(o, w));                              // 2 X[k]
+            const float pw = x.x * x.x + x.y * x.y;                        // 4 |X[k]|^2
+#define FOLD(T, NOTE, LO, HI) \
+            if (t == T && lane >= LO && lane < HI) acc[NOTE] += pw;
+#include "fp_chroma_fold.inc"
+#undef FOLD
         }
-        __syncwarp();
-        float sums[FP_BANDS];
 #pragma unroll
         for (int b = 0; b < FP_BANDS; b++) {
-            float s = acc[b * 32 + lane];
+            float s = acc[b];
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            sums[b] = s;
+            acc[b] = 0.25f * s;
         }
         if (lane == 0) {
             float4 *out = reinterpret_cast<float4 *>(a.chroma + (uint64_t)frame * FP_BANDS);
-            out[0] = make_float4(sums[0], sums[1], sums[2], sums[3]);
-            out[1] = make_float4(sums[4], sums[5], sums[6], sums[7]);
-            out[2] = make_float4(sums[8], sums[9], sums[10], sums[11]);
+            out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            out[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
         }
-        __syncwarp();
     }
 }
 
@@ -464,19 +536,6 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
         set_last_error_msg("chroma bin range does not match the kernel's compiled range");
         return NB200_ERR_STATE;
     }
-    std::vector<uint32_t> notes(6 * 32, 0);
-    for (int l = 0; l < 32; l++)
-        for (int t = 0; t < 48; t++) {
-            const int k = l + 32 * t;
-            uint32_t note = 12;
-            if (t < FP_T && k >= min_index && k < max_index) {
-                const double freq = (double)k * FP_SAMPLE_RATE / FP_FRAME;
-                const double octave = log(freq / (440.0 / 16.0)) / log(2.0);
-                note = (uint32_t)(int)(FP_BANDS * (octave - floor(octave)));
-            }
-            notes[(t >> 3) * 32 + l] |= note << (4 * (t & 7));
-        }
-
     K2Classifier cls[FP_NUM_CLASSIFIERS];
     for (int k = 0; k < FP_NUM_CLASSIFIERS; k++) {
         const FpClassifierDef &d = FP_CLASSIFIERS_TEST2[k];
@@ -485,18 +544,23 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpyToSymbol(c_w64, w64.data(), sizeof(float2) * 64));
     NB_CUDA(cudaMemcpyToSymbol(c_w32, w32.data(), sizeof(float2) * 32));
     NB_CUDA(cudaMemcpyToSymbol(c_w128, w128.data(), sizeof(float2) * FP_T));
+    auto rot = [](std::vector<float2> v) {
+        for (auto &w : v) w = make_float2(-w.y, w.x);
+        return v;
+    };
+    NB_CUDA(cudaMemcpyToSymbol(c_w64r, rot(w64).data(), sizeof(float2) * 64));
+    NB_CUDA(cudaMemcpyToSymbol(c_w32r, rot(w32).data(), sizeof(float2) * 32));
+    NB_CUDA(cudaMemcpyToSymbol(c_w128r, rot(w128).data(), sizeof(float2) * FP_T));
     NB_CUDA(cudaMemcpyToSymbol(c_cls, cls, sizeof(cls)));
     NB_CUDA(cudaMemcpyToSymbol(c_fir, FP_FIR_COEFFS, sizeof(double) * FP_FIR_LEN));
     NB_TRY(ctx->d_fp_window.alloc(sizeof(float2) * FP_HALF));
     NB_TRY(ctx->d_fp_twiddle.alloc(sizeof(float2) * FP_HALF));
     NB_TRY(ctx->d_fp_lane.alloc(sizeof(float2) * 32));
-    NB_TRY(ctx->d_fp_notes.alloc(sizeof(uint32_t) * 6 * 32));
     NB_CUDA(cudaMemcpy(ctx->d_fp_window.p, window.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_twiddle.p, tw.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_lane.p, lane_w.data(), sizeof(float2) * 32, cudaMemcpyHostToDevice));
-    NB_CUDA(cudaMemcpy(ctx->d_fp_notes.p, notes.data(), sizeof(uint32_t) * 6 * 32, cudaMemcpyHostToDevice));
-    const int smem = (int)(sizeof(float2) * (2 * FP_HALF + FP_WARPS * XCHG_ELEMS));
-    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 K1_SMEM_BYTES));
     ctx->fp_ready = true;
     return NB200_OK;
 }
@@ -591,11 +655,10 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
         k1.window = ctx->d_fp_window.as<float2>();
         k1.twiddle = ctx->d_fp_twiddle.as<float2>();
         k1.lane_w = ctx->d_fp_lane.as<float2>();
-        k1.notes = ctx->d_fp_notes.as<uint32_t>();
         k1.chroma = ctx->d_chroma.as<float>();
         const uint32_t n_blocks = (uint32_t)((frames + FP_WARPS - 1) / FP_WARPS);
         const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, n_blocks);
-        const size_t smem = sizeof(float2) * (2 * FP_HALF + FP_WARPS * XCHG_ELEMS);
+        const size_t smem = K1_SMEM_BYTES;
         NB_CUDA_F(cudaEventRecord(ctx->ev[0], st));
         fp_fft_chroma_kernel<<<grid1, FP_WARPS * 32, smem, st>>>(k1);
         NB_CUDA_F(cudaGetLastError());

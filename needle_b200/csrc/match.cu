@@ -44,6 +44,7 @@ constexpr int MATCH_WARPS = 4;        // warps per CTA (independent workers)
 constexpr int SRC_TILE = MATCH_R + 8;             // rows r0-4 .. r0+R+3
 constexpr int DST_TILE = MATCH_R + MATCH_DW + 8;  // cols tile_j0 .. tile_j0+R+263
 constexpr int LUT_SHIFT = 7;
+constexpr int FAST_DST_TILE = 2 * MATCH_R;        // fast kernel: s = 255 + kk - x in [0, 510]
 constexpr int FOREIGN = -(1 << 30);   // carry marker: run started in an earlier chunk
 
 struct MatchProblem {
@@ -331,6 +332,168 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchA
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fast variant for lcand >= 63 (every default configuration: 20 s / 0.246 s = 82
+// cells).  A run that long contains at least one ALIGNED 32-row word of its
+// diagonal in which all 32 cells match, so the hot loop only has to find such
+// words: per (32 rows x diagonal) the MAXIMUM Hamming distance, one 3-input
+// max per two cells -- no match words, no run bookkeeping, no FLO/BREV on the
+// XU pipe that POPC needs.  A full word is handed to the whole warp, which
+// walks the diagonal backwards (is this the run's first full word? only that
+// one owns the run) and forwards (where does it end?) 32 cells per ballot.
+__device__ __noinline__ void coop_long_run(const EmitCtx a, uint32_t problem, int i0, int d, int lane) {
+    const MatchProblem pr = a.problems[problem];
+    const uint32_t *hs = a.hashes + pr.src_off;
+    const uint32_t *hd = a.hashes + pr.dst_off;
+    const int n = (int)pr.n, m = (int)pr.m;
+    // cells (i0-1-lane, .) : contiguous matches going up from the word
+    bool mt = false;
+    {
+        const int i = i0 - 1 - lane, j = i - d;
+        if (i >= 1 && j >= 1 && j <= m - 1) mt = hamming_match(hs[i], hd[j], a.threshold);
+    }
+    const uint32_t up = __ballot_sync(0xffffffffu, mt);
+    if (up == 0xffffffffu) return;                 // the aligned word above is full too: it owns the run
+    const int above = __ffs((int)~up) - 1;
+    const int i_first = i0 - above;
+    int len = 32 + above;
+    int base = i0 + 32;
+    for (;;) {
+        const int i = base + lane, j = i - d;
+        bool f = false;
+        if (i <= n - 1 && j >= 1 && j <= m - 1) f = hamming_match(hs[i], hd[j], a.threshold);
+        const uint32_t fw = __ballot_sync(0xffffffffu, f);
+        if (fw == 0xffffffffu) {
+            len += 32;
+            base += 32;
+            continue;
+        }
+        len += __ffs((int)~fw) - 1;
+        break;
+    }
+    // first matching row = i0 - (cells above the word); last = first + len - 1
+    if (lane == 0) check_emit(a, problem, i_first + len - 1, d, len);
+}
+
+//
+// Geometry: diagonals are WRAPPED modulo (m - 1).  Column 0 never matches, so a
+// row has m - 1 live columns j = 1 .. m-1; wrapped diagonal u holds the cells
+// j - 1 = (i - 1 - u) mod (m - 1).  A 256-row chunk then needs exactly
+// ceil((m-1)/256) warp tiles with no empty triangles at either end (the plain
+// diagonal tiling of the general kernel computes ~19 % dead cells on the
+// BASELINE shapes).  A word that contains the wrap point, row 0, rows past n-1
+// or a duplicate diagonal (u >= m-1 in the last band) can look full without
+// being a run; those are filtered where a full word is reported (rare), so the
+// hot loop has no boundary handling at all.
+__global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const MatchArgs a) {
+    __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][MATCH_R];
+    __shared__ __align__(16) uint32_t s_dst[MATCH_WARPS][FAST_DST_TILE];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *src_t = s_src[warp];
+    uint32_t *dst_t = s_dst[warp];
+    const int T = (int)a.threshold;
+    const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
+
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.n_tiles) break;
+
+        uint32_t p = a.lut[tile >> LUT_SHIFT];
+        while (tile >= a.tile_end[p]) p++;
+        const MatchProblem pr = a.problems[p];
+        const int n = (int)pr.n, M = (int)pr.m - 1;   // M live columns
+        const uint32_t local = tile - pr.tile_begin;
+        const int chunk = (int)(local / pr.n_bands);
+        const int band = (int)(local - (uint32_t)chunk * pr.n_bands);
+        const int r0 = chunk * MATCH_R;
+        const int ub = band * MATCH_DW;
+        // dst_t[s] = dst[1 + ((e0 + s) mod M)],  cell (row r0+kk, diagonal ub+x) <-> s = 255 + kk - x
+        int e0 = (r0 - 1 - (ub + MATCH_DW - 1)) % M;
+        if (e0 < 0) e0 += M;
+
+        __syncwarp();
+        {
+            const uint32_t *hs = a.hashes + pr.src_off;
+            const uint32_t *hd = a.hashes + pr.dst_off + 1;
+            for (int s = lane; s < MATCH_R; s += 32) {
+                const int i = r0 + s;
+                src_t[s] = i < n ? hs[i] : 0u;
+            }
+            int idx = (e0 + lane) % M;
+            const int inc = 32 % M;
+            for (int s = lane; s < FAST_DST_TILE; s += 32) {
+                dst_t[s] = hd[idx];
+                idx += inc;
+                if (idx >= M) idx -= M;
+            }
+        }
+        __syncwarp();
+
+        const int n_steps = min(MATCH_R / 32, (n - r0 + 31) / 32);
+        for (int step = 0; step < n_steps; step++) {
+            const uint4 *dptr = reinterpret_cast<const uint4 *>(dst_t + (248 + 32 * step - MATCH_C * lane));
+            const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
+            uint32_t dw[40];
+#pragma unroll
+            for (int q = 0; q < 10; q++) {
+                const uint4 v = dptr[q];
+                dw[4 * q + 0] = v.x;
+                dw[4 * q + 1] = v.y;
+                dw[4 * q + 2] = v.z;
+                dw[4 * q + 3] = v.w;
+            }
+            int mx[MATCH_C];
+#pragma unroll
+            for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint4 sv = sptr[q];
+                const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int kk = 0; kk < 4; kk += 2) {
+                    const int k = 4 * q + kk;
+#pragma unroll
+                    for (int c = 0; c < MATCH_C; c++) {
+                        // cell (row k, diagonal c of this lane): window element k + 7 - c
+                        const int p0 = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]);
+                        const int p1 = __popc(s4[kk + 1] ^ dw[k + 1 + (MATCH_C - 1) - c]);
+                        mx[c] = max(mx[c], max(p0, p1));     // one 3-input max per two cells
+                    }
+                }
+            }
+            int best = mx[0];
+#pragma unroll
+            for (int c = 1; c < MATCH_C; c++) best = min(best, mx[c]);
+            // ---- rare: some diagonal of some lane has 32 matching cells in a row
+            uint32_t pending = __ballot_sync(0xffffffffu, best <= T);
+            if (pending == 0) continue;
+            uint32_t full = 0;
+#pragma unroll
+            for (int c = 0; c < MATCH_C; c++) full |= (mx[c] <= T ? 1u : 0u) << c;
+            const int i0 = r0 + 32 * step;
+            while (pending) {
+                const int src_lane = __ffs((int)pending) - 1;
+                pending &= pending - 1;
+                uint32_t f = __shfl_sync(0xffffffffu, full, src_lane);
+                while (f) {
+                    const int c = __ffs((int)f) - 1;
+                    f &= f - 1;
+                    const int u = ub + src_lane * MATCH_C + c;
+                    if (u >= M || i0 == 0 || i0 + 31 > n - 1) continue;     // duplicate diagonal / row 0 / past the end
+                    int jm = (i0 - 1 - u) % M;                              // j0 - 1
+                    if (jm < 0) jm += M;
+                    if (jm + 31 > M - 1) continue;                          // the wrap point is inside the word
+                    coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
+                }
+            }
+        }
+    }
+}
+
 // K4: simhash32 of both sides of every emitted run (comparator.rs:149-153,
 // 226-229): per-bit majority over hashes[i_end-len ..= i_end], ties -> 0.
 // One warp per run; lane b counts bit b.
@@ -395,6 +558,17 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         lmin[s] = min_qualifying_len(hs->h_ts.data() + hs->seg_offset[s], hs->seg_len[s], mn);
     }
 
+    // the fast kernel needs every qualifying run to span a full aligned 32-row word
+    uint32_t min_lcand = 0xffffffffu;
+    for (uint64_t k = 0; k < n_pairs; k++) {
+        const uint32_t a = pairs[k][0], b = pairs[k][1];
+        if (a >= hs->n_videos || b >= hs->n_videos) return NB200_ERR_INVALID_ARGUMENT;
+        for (int e = 0; e < (endings ? 2 : 1); e++)
+            if (hs->seg_len[2 * a + e] >= 2 && hs->seg_len[2 * b + e] >= 2)
+                min_lcand = std::min(min_lcand, std::max(1u, std::max(lmin[2 * a + e], lmin[2 * b + e])));
+    }
+    const bool fast = min_lcand >= 63 && !ctx->force_general_match;
+
     auto rs = new nb200_runset();
     std::vector<MatchProblem> problems;
     problems.reserve(n_pairs * (endings ? 2 : 1));
@@ -423,7 +597,8 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
             pr.lcand = std::max(1u, std::max(lmin[sa], lmin[sb]));
             const uint64_t chunks = (n + MATCH_R - 1) / MATCH_R;
             // diagonals per chunk: (m-1) + (R-1) + up to 3 of alignment slack
-            pr.n_bands = (uint32_t)(((uint64_t)m + MATCH_R + 1 + MATCH_DW - 1) / MATCH_DW);
+            pr.n_bands = fast ? (uint32_t)(((uint64_t)m - 1 + MATCH_DW - 1) / MATCH_DW)
+                              : (uint32_t)(((uint64_t)m + MATCH_R + 1 + MATCH_DW - 1) / MATCH_DW);
             pr.tile_begin = (uint32_t)tiles;
             pr.pad = 0;
             tiles += chunks * pr.n_bands;
@@ -509,7 +684,10 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         uint32_t grid = (uint32_t)ctx->sm_count * 4;
         grid = std::min<uint32_t>(grid, (warps_needed + MATCH_WARPS - 1) / MATCH_WARPS);
         NB_CUDA_F(cudaEventRecord(ctx->ev[4], s));
-        match_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        if (fast)
+            match_fast_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        else
+            match_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
         NB_CUDA_F(cudaGetLastError());
         NB_CUDA_F(cudaEventRecord(ctx->ev[5], s));
         ctx->ev_valid[2] = true;

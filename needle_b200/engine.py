@@ -67,6 +67,9 @@ class Context:
         check(lib().nb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None),
               "nb200_ctx_set_stream")
 
+    def set_option(self, option: int, value: int):
+        check(lib().nb200_ctx_set_option(self._h, option, value), "nb200_ctx_set_option")
+
     def synchronize(self):
         check(lib().nb200_ctx_synchronize(self._h), "nb200_ctx_synchronize")
 

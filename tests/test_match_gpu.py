@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
+from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -20,6 +20,12 @@ def check_season(ctx, orc, season, **kw):
     p = engine.match_params(**kw)
     runs = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, p)
     assert H.runs_as_rows(runs) == H.entries_as_runs(entries)
+    # the general kernel gives the same list where the fast variant was eligible
+    ctx.set_option(OPT_FORCE_GENERAL_MATCH, 1)
+    try:
+        assert np.array_equal(ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, p), runs)
+    finally:
+        ctx.set_option(OPT_FORCE_GENERAL_MATCH, 0)
     got = ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, p)
     assert got == want_results
     # device-resident path gives the same answer
@@ -83,6 +89,31 @@ def test_runs_cross_row_chunks(ctx, oracle):
     H.plant(rng, season, 120, [(0, 950), (5, 30)])
     check_season(ctx, oracle, season)
     check_season(ctx, oracle, season, min_opening_ns=0)
+
+
+def test_fast_kernel_word_ownership(ctx, oracle):
+    """Runs of every length 60..140 at every alignment mod 32 (the fast kernel finds a
+    run through its first fully matching aligned 32-row word), plus runs of many
+    words and runs that touch the table edges."""
+    rng = np.random.default_rng(21)
+    n = 1500
+    vids = [rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32) for _ in range(4)]
+    pos = 5
+    for k, ln in enumerate(range(60, 141, 3)):
+        base = rng.integers(0, 2 ** 32, ln, dtype=np.uint64).astype(np.uint32)
+        a, b = pos + (k % 32), 900 - pos + (7 * k) % 32
+        if a + ln < n - 2 and b + ln < n - 2 and b > 1:
+            vids[0][a:a + ln] = base
+            vids[1][b:b + ln] = base
+        pos += ln // 4 + 11
+    long_run = rng.integers(0, 2 ** 32, 700, dtype=np.uint64).astype(np.uint32)
+    vids[2][1:701] = long_run            # starts at index 1 (row 0 never matches)
+    vids[3][n - 700:] = long_run         # ends at the last column
+    ts = synth.hash_timestamps(2 * n, 2)[:n]
+    season = H.season_from_lists([(v, ts) for v in vids], [(np.zeros(0, np.uint32), np.zeros(0, np.uint64))] * 4)
+    runs, _ = check_season(ctx, oracle, season, threshold=0)
+    assert len(runs) >= 15
+    check_season(ctx, oracle, season, threshold=0, min_opening_ns=16_000_000_000)    # lcand 66
 
 
 def test_threshold_extremes(ctx, oracle):

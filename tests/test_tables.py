@@ -34,3 +34,19 @@ def test_scalar_constants_agree():
     assert val(prod, "FP_MAX_FREQ") == val(orc, "ORC_MAX_FREQ") == "3520"
     assert val(prod, "FP_FIR_LEN") == val(orc, "ORC_CHROMA_FILTER_LEN") == "5"
     assert "{0.25, 0.75, 1.0, 0.75, 0.25}" in prod and "{0.25, 0.75, 1.0, 0.75, 0.25}" in orc
+
+
+def test_generated_chroma_fold_matches_oracle_notes():
+    """needle_b200/csrc/fp_chroma_fold.inc (compile-time pitch classes of K1) against
+    the oracle's Chroma::PrepareNotes table: every bin in [10, 1308) exactly once."""
+    from oracle import oracle as orc
+    lo, hi, notes = orc.chroma_notes()
+    src = open(os.path.join(ROOT, "needle_b200/csrc/fp_chroma_fold.inc")).read()
+    seen = {}
+    for t, n, a, b in re.findall(r"FOLD\((\d+), (\d+), (\d+), (\d+)\)", src):
+        for lane in range(int(a), int(b)):
+            k = lane + 32 * int(t)
+            assert k not in seen
+            seen[k] = int(n)
+    assert sorted(seen) == list(range(lo, hi))
+    assert all(seen[k] == int(notes[k]) for k in seen)
