@@ -40,7 +40,7 @@ EPISODES = 28
 MINUTES = 20.0
 FLOP_PER_FRAME = 134.6e3        # 4096-pt real FFT + window + power + fold + classify
 BYTES_PER_FRAME = 1365 * 2 + 4  # mono i16 in (one hop) + one u32 hash out
-POPC_PER_CLK_PER_SM = 23.7      # measured on this pool (profiles/r01_pipe_peak*.jsonl), not the 16 of the CUDA guide
+POPC_PER_CLK_PER_SM = 16.0      # XU pipe; tools/pipe_peak.cu measures 15.0 at 1965 MHz (profiles/r01_pipe_peak_warm.jsonl)
 
 
 def parse_args():
@@ -431,7 +431,8 @@ def run_b200(args):
             "kernel": "match", "bound": "int_popc", "unit": "Tcell/s",
             "achieved": cells_local / k3_s / 1e12,
             "peak": popc_peak_nominal,
-            "peak_source": "measured POPC issue rate %.1f/clk/SM (tools/pipe_peak.cu) x 148 SM x 1965 MHz" % POPC_PER_CLK_PER_SM,
+            "peak_source": "POPC issue rate %.0f/clk/SM x 148 SM x 1965 MHz (pure POPC loop measures 4.33 T/s, "
+                           "profiles/r01_pipe_peak_warm.jsonl)" % POPC_PER_CLK_PER_SM,
             "peak_at_measured_clock": 148 * POPC_PER_CLK_PER_SM * sm_mhz * 1e6 / 1e12,
             "cells_per_launch": cells_local,
         },

@@ -110,6 +110,11 @@ typedef struct nb200_run {
     uint32_t src_simhash; /* simhash32(src[i_end-len ..= i_end]) (comparator.rs:149-153) */
     uint32_t dst_simhash;
     uint32_t reserved;
+    /* src_longest_run / dst_longest_run (comparator.rs:208-209,233-234), ns */
+    uint64_t src_start_ns; /* ts_src[i_end - len] */
+    uint64_t src_end_ns;   /* ts_src[i_end] */
+    uint64_t dst_start_ns; /* ts_dst[j_end - len] */
+    uint64_t dst_end_ns;   /* ts_dst[j_end] */
 } nb200_run;
 
 /* SearchResult (comparator.rs:65-69) with the video index kept: element v
@@ -152,9 +157,9 @@ int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t
 
 /* Host-only tail of nb200_search for callers that gathered runs themselves
  * (multi-GPU: every rank matches its share of the pair list, rank 0 votes).
- * runs must be sorted as nb200_match_pairs returns them; pairs as above. */
-int nb200_vote(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
-               const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+ * runs must be sorted as nb200_match_pairs returns them; pairs as above.  A run
+ * record carries its own timestamps, so no hash or timestamp array is needed. */
+int nb200_vote(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
                uint64_t n_runs, nb200_search_result *results);
 

@@ -45,12 +45,15 @@ class MatchParams(C.Structure):
 class Run(C.Structure):
     _fields_ = [("pair", C.c_uint32), ("is_ending", C.c_uint32), ("i_end", C.c_uint32),
                 ("j_end", C.c_uint32), ("len", C.c_uint32), ("src_simhash", C.c_uint32),
-                ("dst_simhash", C.c_uint32), ("reserved", C.c_uint32)]
+                ("dst_simhash", C.c_uint32), ("reserved", C.c_uint32),
+                ("src_start_ns", C.c_uint64), ("src_end_ns", C.c_uint64),
+                ("dst_start_ns", C.c_uint64), ("dst_end_ns", C.c_uint64)]
 
 
 RUN_DTYPE = np.dtype([("pair", "<u4"), ("is_ending", "<u4"), ("i_end", "<u4"), ("j_end", "<u4"),
                       ("len", "<u4"), ("src_simhash", "<u4"), ("dst_simhash", "<u4"),
-                      ("reserved", "<u4")])
+                      ("reserved", "<u4"), ("src_start_ns", "<u8"), ("src_end_ns", "<u8"),
+                      ("dst_start_ns", "<u8"), ("dst_end_ns", "<u8")])
 
 
 class SearchResultC(C.Structure):
@@ -86,7 +89,7 @@ PROTOTYPES = {
     "nb200_search": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.POINTER(MatchParams),
                                C.POINTER(SearchResultC)]),
     "nb200_search_hashset": (C.c_int, [_P, _P, _P, C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
-    "nb200_vote": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, C.c_uint64, C.POINTER(MatchParams),
+    "nb200_vote": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, C.POINTER(MatchParams),
                              _P, C.c_uint64, C.POINTER(SearchResultC)]),
     "nb200_hashset_upload": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _PP]),
     "nb200_hashset_info": (C.c_int, [_P, C.POINTER(C.c_uint32), _U64P, _P]),

@@ -248,8 +248,6 @@ int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t 
         delete hs;
         return st;
     }
-    hs->h_ts.assign(ts_ns, ts_ns + total);
-    hs->ts_on_host = true;
     // stage in the aligned layout (pad entries are zero and never read unmasked)
     const size_t b_h = (size_t)hs->dev_total * sizeof(uint32_t);
     const size_t b_t = (size_t)hs->dev_total * sizeof(uint64_t);
@@ -381,7 +379,6 @@ int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *
         delete hs;
         return st;
     }
-    hs->ts_on_host = false;   // mirrored lazily by the match stage
     *out = hs;
     return NB200_OK;
 }
@@ -433,7 +430,6 @@ int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, co
         delete hs;
         return st;
     }
-    hs->ts_on_host = false;
     *out = hs;
     return NB200_OK;
 }
@@ -483,6 +479,10 @@ int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *run
         o.src_simhash = r.src_simhash;
         o.dst_simhash = r.dst_simhash;
         o.reserved = 0;
+        o.src_start_ns = r.src_start_ns;
+        o.src_end_ns = r.src_end_ns;
+        o.dst_start_ns = r.dst_start_ns;
+        o.dst_end_ns = r.dst_end_ns;
     }
     return NB200_OK;
 }
@@ -516,14 +516,12 @@ int nb200_match_pairs(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts
     return st;
 }
 
-int nb200_vote(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
-               const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+int nb200_vote(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
                uint64_t n_runs, nb200_search_result *results) {
-    if (!seg_offset || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
-    if (n_runs > 0 && (!runs || !ts_ns)) return NB200_ERR_NULL_ARGUMENT;
-    return vote_impl(hashes, ts_ns, seg_offset, hash_duration_ns, n_videos, pairs, n_pairs, params, runs,
-                     n_runs, results);
+    if (!hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_runs > 0 && !runs) return NB200_ERR_NULL_ARGUMENT;
+    return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs, n_runs, results);
 }
 
 int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
@@ -534,8 +532,7 @@ int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
     nb200_run *runs = nullptr;
     uint64_t n_runs = 0;
     NB_TRY(nb200_match_pairs(ctx, hashes, ts_ns, seg_offset, n_videos, nullptr, 0, params, &runs, &n_runs));
-    int st = vote_impl(hashes, ts_ns, seg_offset, hash_duration_ns, n_videos, nullptr, 0, params, runs,
-                       n_runs, results);
+    int st = vote_impl(hash_duration_ns, n_videos, nullptr, 0, params, runs, n_runs, results);
     free(runs);
     return st;
 }
@@ -551,10 +548,8 @@ int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t
     NB_TRY(nb200_match_run(ctx, hs, nullptr, 0, params, &rs));
     std::vector<nb200_run> runs(std::max<uint64_t>(rs->n_runs, 1));
     int st = nb200_runset_download(ctx, rs, runs.data());
-    // match_run_impl mirrored the timestamps on the host already
     if (st == NB200_OK)
-        st = vote_impl(nullptr, hs->h_ts.data(), hs->seg_offset.data(), hash_duration_ns, hs->n_videos,
-                       nullptr, 0, params, runs.data(), rs->n_runs, results);
+        st = vote_impl(hash_duration_ns, hs->n_videos, nullptr, 0, params, runs.data(), rs->n_runs, results);
     nb200_runset_free(rs);
     return st;
 }

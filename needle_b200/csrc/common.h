@@ -151,7 +151,7 @@ struct nb200_ctx {
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
-    nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_runs_sorted;
+    nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
     nb200::PinnedBuf h_stage, h_small;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
@@ -166,19 +166,9 @@ struct nb200_hashset {
     std::vector<uint64_t> seg_offset;   // caller's packed offsets [2N+1]
     std::vector<uint32_t> dev_offset;   // aligned device offsets [2N]
     std::vector<uint32_t> seg_len;      // [2N]
-    std::vector<uint32_t> seg_lmin_open, seg_lmin_end;  // filled lazily per params
     uint64_t total = 0;                 // packed element count
     uint64_t dev_total = 0;             // aligned element count
     nb200::DevBuf d_hashes, d_ts;
-    // host mirrors of the timestamps (needed for the run-length lower bound);
-    // empty when the set was produced on the device and not yet mirrored
-    std::vector<uint64_t> h_ts;
-    bool ts_on_host = false;
-    // timestamps follow the analyzer formula with these parameters (device-made sets)
-    bool ts_formula = false;
-    uint64_t delay_ns = 0, item_ns = 0;
-    uint32_t stride = 1;
-    std::vector<uint64_t> seek_to_ns;   // [2N]
 };
 
 struct nb200_pcmset {
@@ -204,6 +194,7 @@ struct DeviceRun {
     uint32_t problem;
     uint32_t i_end, j_end, len;
     uint32_t src_simhash, dst_simhash;
+    uint64_t src_start_ns, src_end_ns, dst_start_ns, dst_end_ns;
 };
 
 int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
@@ -211,13 +202,9 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pai
 
 // vote.cpp ---------------------------------------------------------------
 void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order
-int vote_impl(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
-              const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
               uint64_t n_runs, nb200_search_result *results);
-// Smallest run length that can satisfy ts[i] - ts[i-len] >= min_ns anywhere in
-// the list (1 if the list is not monotone, so that every run is examined).
-uint32_t min_qualifying_len(const uint64_t *ts, size_t n, uint64_t min_ns);
 
 // fingerprint.cu -----------------------------------------------------------
 int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,

@@ -616,11 +616,6 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
         }
         hs->total = seg_offset[nseg];
         hs->dev_total = dev;
-        hs->ts_on_host = false;
-        hs->ts_formula = true;
-        hs->delay_ns = delay_ns;
-        hs->item_ns = item_ns;
-        hs->stride = stride;
     }
     if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
         hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK)

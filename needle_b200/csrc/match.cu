@@ -26,8 +26,8 @@
 //
 // The duration filter of :212-223 is evaluated exactly, on the u64 ns
 // timestamps, for every run that reaches `lcand` cells -- a per-problem lower
-// bound on the length of any qualifying run computed on the host from the same
-// timestamps (vote.cpp: min_qualifying_len).  Runs shorter than that cannot
+// bound on the length of any qualifying run computed from the same
+// timestamps on the device (seg_lmin_kernel).  Runs shorter than that cannot
 // pass the filter, so skipping them changes nothing.
 #include <algorithm>
 #include <cstring>
@@ -110,6 +110,10 @@ __device__ __noinline__ void check_emit(const EmitCtx a, uint32_t problem, int i
             r.len = (uint32_t)len;
             r.src_simhash = 0;
             r.dst_simhash = 0;
+            r.src_start_ns = s_start;
+            r.src_end_ns = s_end;
+            r.dst_start_ns = d_start;
+            r.dst_end_ns = d_end;
             a.runs[slot] = r;
         }
     }
@@ -530,17 +534,54 @@ __global__ void __launch_bounds__(128) simhash_kernel(const uint32_t *__restrict
     }
 }
 
-// ------------------------------------------------------------------- host
+// Per segment: the smallest run length that can satisfy ts[i] - ts[i-len] >= min
+// anywhere in the list (comparator.rs:212-218 only ever compares timestamps of
+// one list).  1 when the list is not monotone (then every run is examined and
+// the underflow the reference would panic on is reported), "longer than the
+// list" when no window qualifies.  One thread per element: binary search for
+// the latest start that is still min apart, atomicMin of the distance.
+struct SegTab {
+    uint32_t dev_offset, len;
+};
+__global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *__restrict__ segs,
+                                uint32_t n_seg, uint64_t dev_total, uint64_t min_open_ns, uint64_t min_end_ns,
+                                uint32_t *__restrict__ lmin) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= dev_total) return;
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (segs[mid].dev_offset <= idx) lo = mid; else hi = mid;
+    }
+    const SegTab sg = segs[lo];
+    const uint32_t i = (uint32_t)(idx - sg.dev_offset);
+    if (i >= sg.len || i == 0) return;
+    const uint64_t *t = ts + sg.dev_offset;
+    const uint64_t mn = (lo & 1) ? min_end_ns : min_open_ns;
+    const uint64_t ti = t[i];
+    if (ti < t[i - 1]) {
+        atomicMin(&lmin[lo], 1u);
+        return;
+    }
+    if (ti < mn || t[0] > ti - mn) return;          // no start is far enough from i
+    // largest s in [0, i-1] with t[s] <= ti - mn  (t[0] qualifies)
+    const uint64_t limit = ti - mn;
+    uint32_t a = 0, b = i;                          // invariant: t[a] <= limit, b = first index known > limit (or i)
+    while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (t[mid] <= limit) a = mid; else b = mid;
+    }
+    const uint32_t len = i - a;
+    atomicMin(&lmin[lo], len < 1u ? 1u : len);
+}
 
-static int ensure_host_ts(nb200_ctx *ctx, nb200_hashset *hs);
+// ------------------------------------------------------------------- host
 
 int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pairs)[2],
                    uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out) {
     nb200_hashset *hs = const_cast<nb200_hashset *>(hs_c);
     if (params->hash_match_threshold > 32) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
-    NB_TRY(ensure_host_ts(ctx, hs));
-
     std::vector<uint32_t> default_flat;
     if (!pairs) {
         default_pairs(hs->n_videos, default_flat);
@@ -548,14 +589,34 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         n_pairs = default_flat.size() / 2;
     }
     const bool endings = params->include_endings != 0;
+    cudaStream_t s = ctx->stream;
 
-    // run-length lower bounds per segment
+    // run-length lower bounds per segment, computed where the timestamps live
     const uint32_t nseg = 2 * hs->n_videos;
     std::vector<uint32_t> lmin(nseg, 1);
-    for (uint32_t s = 0; s < nseg; s++) {
-        if ((s & 1) && !endings) continue;
-        const uint64_t mn = (s & 1) ? params->min_ending_ns : params->min_opening_ns;
-        lmin[s] = min_qualifying_len(hs->h_ts.data() + hs->seg_offset[s], hs->seg_len[s], mn);
+    if (nseg > 0 && hs->dev_total > 0) {
+        const size_t b_tab = (size_t)nseg * sizeof(SegTab), b_lmin = (size_t)nseg * sizeof(uint32_t);
+        if (ctx->h_stage.reserve(b_tab + b_lmin) != NB200_OK || ctx->d_segtab.reserve(b_tab) != NB200_OK ||
+            ctx->d_lmin.reserve(b_lmin) != NB200_OK)
+            return NB200_ERR_CUDA;
+        SegTab *tab = ctx->h_stage.as<SegTab>();
+        uint32_t *init = reinterpret_cast<uint32_t *>(tab + nseg);
+        for (uint32_t k = 0; k < nseg; k++) {
+            tab[k] = {hs->dev_offset[k], hs->seg_len[k]};
+            const uint64_t mn = (k & 1) ? params->min_ending_ns : params->min_opening_ns;
+            // n < 2 or min == 0: every run is a candidate; else start from "no window qualifies"
+            init[k] = (hs->seg_len[k] < 2 || mn == 0) ? 1u : std::min<uint32_t>(hs->seg_len[k], 0x7fffffffu);
+        }
+        NB_CUDA(cudaMemcpyAsync(ctx->d_segtab.p, tab, b_tab, cudaMemcpyHostToDevice, s));
+        NB_CUDA(cudaMemcpyAsync(ctx->d_lmin.p, init, b_lmin, cudaMemcpyHostToDevice, s));
+        seg_lmin_kernel<<<(unsigned)((hs->dev_total + 255) / 256), 256, 0, s>>>(
+            hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), nseg, hs->dev_total, params->min_opening_ns,
+            params->min_ending_ns, ctx->d_lmin.as<uint32_t>());
+        NB_CUDA(cudaGetLastError());
+        ctx->n_launches++;
+        NB_CUDA(cudaMemcpyAsync(init, ctx->d_lmin.p, b_lmin, cudaMemcpyDeviceToHost, s));
+        NB_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t k = 0; k < nseg; k++) lmin[k] = std::max(1u, init[k]);
     }
 
     // the fast kernel needs every qualifying run to span a full aligned 32-row word
@@ -649,7 +710,6 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
     memcpy(st, problems.data(), b_prob);
     memcpy(st + b_prob, tile_end.data(), b_tend);
     memcpy(st + b_prob + b_tend, lut.data(), b_lut);
-    cudaStream_t s = ctx->stream;
 #define NB_CUDA_F(expr)                          \
     do {                                         \
         cudaError_t _e = (expr);                 \
@@ -718,23 +778,6 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
     }
 #undef NB_CUDA_F
     *out = rs;
-    return NB200_OK;
-}
-
-// Timestamps of a device-made set follow the analyzer formula; mirror them on
-// the host once (only the run-length lower bound needs them).
-static int ensure_host_ts(nb200_ctx *ctx, nb200_hashset *hs) {
-    if (hs->ts_on_host) return NB200_OK;
-    hs->h_ts.resize(hs->total);
-    // Device layout is aligned per segment: copy segment by segment.
-    std::vector<uint64_t> tmp(hs->dev_total);
-    NB_CUDA(cudaMemcpyAsync(tmp.data(), hs->d_ts.p, hs->dev_total * sizeof(uint64_t),
-                            cudaMemcpyDeviceToHost, ctx->stream));
-    NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t s = 0; s < 2 * hs->n_videos; s++)
-        memcpy(hs->h_ts.data() + hs->seg_offset[s], tmp.data() + hs->dev_offset[s],
-               (size_t)hs->seg_len[s] * sizeof(uint64_t));
-    hs->ts_on_host = true;
     return NB200_OK;
 }
 

@@ -9,6 +9,7 @@
 //   * info_map and find_best_match                 (:580-588, :405-515)
 //
 // Pure C++ (no CUDA): also used by rank 0 of a multi-GPU job on gathered runs.
+// Every run record carries its four timestamps, so nothing else is read.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -31,27 +32,6 @@ void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat) {
         }
         processed[i] = 1;
     }
-}
-
-uint32_t min_qualifying_len(const uint64_t *ts, size_t n, uint64_t min_ns) {
-    if (n < 2) return 1;
-    for (size_t i = 1; i < n; i++)
-        if (ts[i] < ts[i - 1]) return 1;   // not monotone: examine every run (underflow semantics)
-    if (min_ns == 0) return 1;
-    // two pointers: for every end i the largest start s with ts[i] - ts[s] >= min_ns
-    size_t best = n;   // "no window qualifies" -> longer than any possible run
-    size_t s = 0;
-    bool have = false;
-    for (size_t i = 1; i < n; i++) {
-        if (ts[i] - ts[0] < min_ns) continue;
-        if (!have) {
-            s = 0;
-            have = true;
-        }
-        while (s + 1 < i && ts[i] - ts[s + 1] >= min_ns) s++;
-        best = std::min(best, i - s);
-    }
-    return (uint32_t)std::max<size_t>(1, std::min<size_t>(best, 0x7fffffff));
 }
 
 namespace {
@@ -99,11 +79,9 @@ struct PairInfo {            // OpeningAndEndingInfo; src_* and dst_* lists hold
 
 }  // namespace
 
-int vote_impl(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
-              const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
               uint64_t n_runs, nb200_search_result *results) {
-    (void)hashes;
     std::vector<uint32_t> default_flat;
     if (!pairs) {
         default_pairs(n_videos, default_flat);
@@ -125,13 +103,11 @@ int vote_impl(const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg
             if (!(key(q) < key(run))) return NB200_ERR_INVALID_ARGUMENT;
         }
         const uint32_t src = pairs[run.pair][0], dst = pairs[run.pair][1];
-        const uint32_t e = run.is_ending ? 1 : 0;
-        const uint64_t *ts_s = ts_ns + seg_offset[2 * src + e];
-        const uint64_t *ts_d = ts_ns + seg_offset[2 * dst + e];
+        if (src >= n_videos || dst >= n_videos) return NB200_ERR_INVALID_ARGUMENT;
         const bool is_opening = !run.is_ending;
-        Entry en(run.len, ts_s[run.i_end - run.len], ts_s[run.i_end], ts_d[run.j_end - run.len],
-                 ts_d[run.j_end], run.src_simhash, run.dst_simhash, is_opening, !is_opening,
-                 is_opening, !is_opening, hash_duration_ns[src], hash_duration_ns[dst]);
+        Entry en(run.len, run.src_start_ns, run.src_end_ns, run.dst_start_ns, run.dst_end_ns,
+                 run.src_simhash, run.dst_simhash, is_opening, !is_opening, is_opening, !is_opening,
+                 hash_duration_ns[src], hash_duration_ns[dst]);
         heap_push(run.is_ending ? infos[run.pair].endings : infos[run.pair].openings, en);
     }
 

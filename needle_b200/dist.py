@@ -165,10 +165,6 @@ class GpuBackend:
         rs.free()
         return runs
 
-    def season_timestamps(self, season):
-        _h, t, off = season.download()
-        return t, off
-
     def alloc_exchange(self, plan: SeasonPlan):
         t = self.torch
         send = t.zeros(plan.block_bytes, dtype=t.uint8, device=self.device)
@@ -178,8 +174,8 @@ class GpuBackend:
     def gather_runs(self, dist, runs, group=None):
         return gather_runs(dist, runs, self.device, self.torch, group)
 
-    def vote(self, ts, off, hash_duration_ns, params, runs, pairs):
-        return self.engine.vote(ts, off, hash_duration_ns, params, runs, pairs=pairs)
+    def vote(self, hash_duration_ns, params, runs, pairs):
+        return self.engine.vote(hash_duration_ns, params, runs, pairs=pairs)
 
     def release(self, obj):
         obj.free()
@@ -278,8 +274,7 @@ class SeasonJob:
         results = None
         if self.rank == 0:
             all_runs = merge_runs(gathered, self.slices)
-            ts, off = b.season_timestamps(season)
-            results = b.vote(ts, off, self.hash_duration_ns, self.params, all_runs, self.pairs)
+            results = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
         b.release(season)
         return results
 

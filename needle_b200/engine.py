@@ -149,17 +149,16 @@ class Context:
         return _results_list(res, n // 2)
 
 
-def vote(ts_ns, seg_offset, hash_duration_ns, params: MatchParams, runs: np.ndarray, pairs=None):
-    """nb200_vote (host only): runs as returned by match_pairs / RunSet.download."""
-    t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
-    off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+def vote(hash_duration_ns, params: MatchParams, runs: np.ndarray, pairs=None):
+    """nb200_vote (host only): runs as returned by match_pairs / RunSet.download;
+    one hash duration per video."""
     hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
     r = np.ascontiguousarray(runs, dtype=RUN_DTYPE)
-    n_videos = (off.size - 1) // 2
+    n_videos = hd.size
     _keep, pp, npairs = _pairs_arg(pairs)
     res = (SearchResultC * max(n_videos, 1))()
-    check(lib().nb200_vote(None, ptr(t), ptr(off), ptr(hd), n_videos, pp, npairs, C.byref(params),
-                           ptr(r), r.shape[0], res), "nb200_vote")
+    check(lib().nb200_vote(ptr(hd), n_videos, pp, npairs, C.byref(params), ptr(r), r.shape[0], res),
+          "nb200_vote")
     return _results_list(res, n_videos)
 
 

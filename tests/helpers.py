@@ -55,16 +55,51 @@ def oracle_run(orc, season, **kw):
 
 
 def entries_as_runs(entries):
-    """Oracle entries -> sorted list of (pair, is_ending, i_end, j_end, len, src_simhash, dst_simhash)
-    in the library's order: pair, opening first, i desc, j desc."""
-    rows = [(int(p), int(e[7]), int(e[10]), int(e[11]), int(e[0]), int(e[5]), int(e[6])) for p, e in entries]
+    """Oracle entries -> sorted list of (pair, is_ending, i_end, j_end, len, src_simhash, dst_simhash,
+    src_start_ns, src_end_ns, dst_start_ns, dst_end_ns) in the library's order: pair, opening first,
+    i desc, j desc."""
+    rows = [(int(p), int(e[7]), int(e[10]), int(e[11]), int(e[0]), int(e[5]), int(e[6]),
+             int(e[1]), int(e[2]), int(e[3]), int(e[4])) for p, e in entries]
     rows.sort(key=lambda r: (r[0], r[1], -r[2], -r[3]))
     return rows
 
 
+RUN_FIELDS = ("pair", "is_ending", "i_end", "j_end", "len", "src_simhash", "dst_simhash",
+              "src_start_ns", "src_end_ns", "dst_start_ns", "dst_end_ns")
+
+
 def runs_as_rows(runs: np.ndarray):
-    return [(int(r["pair"]), int(r["is_ending"]), int(r["i_end"]), int(r["j_end"]), int(r["len"]),
-             int(r["src_simhash"]), int(r["dst_simhash"])) for r in runs]
+    cols = [runs[f].tolist() for f in RUN_FIELDS]
+    return list(zip(*cols))
+
+
+def rows_to_runs(rows):
+    from needle_b200._lib import RUN_DTYPE
+    runs = np.zeros(len(rows), dtype=RUN_DTYPE)
+    for k, f in enumerate(RUN_FIELDS):
+        runs[f] = [r[k] for r in rows]
+    return runs
+
+
+def oracle_pair_runs(orc, season, pairs=None, **kw):
+    """Run lists only (no vote): orc.longest_common_hash_match per pair, in the
+    library's order.  For cases where the vote's O(candidates^2) would dominate."""
+    n = season.n_videos
+    if pairs is None:
+        pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    off = season.seg_offset.astype(np.int64)
+    rows = []
+    for k, (a, b) in enumerate(pairs):
+        for e in ((0, 1) if kw.get("include_endings") else (0,)):
+            sa, sb = 2 * a + e, 2 * b + e
+            ent = orc.longest_common_hash_match(
+                season.hashes[off[sa]:off[sa + 1]], season.ts_ns[off[sa]:off[sa + 1]],
+                season.hashes[off[sb]:off[sb + 1]], season.ts_ns[off[sb]:off[sb + 1]],
+                threshold=kw.get("threshold", 10), min_opening_ns=kw.get("min_opening_ns", 20_000_000_000),
+                min_ending_ns=kw.get("min_ending_ns", 20_000_000_000), is_opening=(e == 0))
+            rows += [(k, e, x[10], x[11], x[0], x[5], x[6], x[1], x[2], x[3], x[4]) for x in ent]
+    rows.sort(key=lambda r: (r[0], r[1], -r[2], -r[3]))
+    return rows
 
 
 def params_kw(threshold=10, include_endings=False, min_opening_ns=20_000_000_000,

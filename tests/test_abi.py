@@ -43,7 +43,7 @@ def test_header_compiles_as_c():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.Run) == 32 and _lib.RUN_DTYPE.itemsize == 32
+    assert C.sizeof(_lib.Run) == 64 and _lib.RUN_DTYPE.itemsize == 64
     assert C.sizeof(_lib.MatchParams) == 32
     assert C.sizeof(_lib.SearchResultC) == 48
     p = _lib.MatchParams()

@@ -96,17 +96,14 @@ class OracleBackend:
                     threshold=params.hash_match_threshold, min_opening_ns=params.min_opening_ns,
                     min_ending_ns=params.min_ending_ns, is_opening=(e == 0))
                 ent.sort(key=lambda x: (-x[10], -x[11]))
-                rows += [(k, e, x[10], x[11], x[0], x[5], x[6], 0) for x in ent]
-        return np.array(rows, dtype=RUN_DTYPE) if rows else np.zeros(0, dtype=RUN_DTYPE)
-
-    def season_timestamps(self, season):
-        return season.ts_ns, season.seg_offset
+                rows += [(k, e, x[10], x[11], x[0], x[5], x[6], x[1], x[2], x[3], x[4]) for x in ent]
+        return H.rows_to_runs(rows)
 
     def gather_runs(self, dist, runs, group=None):
         return nd.gather_runs(dist, runs, "cpu", self.torch, group)
 
-    def vote(self, ts, off, hd, params, runs, pairs):
-        return engine.vote(ts, off, hd, params, runs, pairs=pairs)
+    def vote(self, hd, params, runs, pairs):
+        return engine.vote(hd, params, runs, pairs=pairs)
 
     def release(self, obj):
         pass

@@ -8,7 +8,6 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import RUN_DTYPE
 from tests import helpers as H
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -29,10 +28,7 @@ def load_match(name):
 
 def golden_runs(entries):
     rows = H.entries_as_runs(entries)
-    runs = np.zeros(len(rows), dtype=RUN_DTYPE)
-    for k, r in enumerate(rows):
-        runs[k] = r + (0,)
-    return rows, runs
+    return rows, H.rows_to_runs(rows)
 
 
 @pytest.mark.parametrize("name", MATCH)
@@ -48,8 +44,7 @@ def test_oracle_reproduces_match_golden(oracle, name):
 def test_host_vote_reproduces_match_golden(name):
     season, kw, entries, results = load_match(name)
     _, runs = golden_runs(entries)
-    assert engine.vote(season.ts_ns, season.seg_offset, season.hash_duration_ns, engine.match_params(**kw),
-                       runs) == results
+    assert engine.vote(season.hash_duration_ns, engine.match_params(**kw), runs) == results
 
 
 @pytest.mark.parametrize("name", FP)

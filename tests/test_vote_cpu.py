@@ -7,15 +7,10 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import RUN_DTYPE
 from tests import helpers as H
 
 
-def rows_to_runs(rows):
-    runs = np.zeros(len(rows), dtype=RUN_DTYPE)
-    for k, r in enumerate(rows):
-        runs[k] = (r[0], r[1], r[2], r[3], r[4], r[5], r[6], 0)
-    return runs
+rows_to_runs = H.rows_to_runs
 
 
 CASES = [
@@ -41,7 +36,7 @@ def test_vote_matches_oracle(oracle, case, seed):
     st, want, entries = H.oracle_run(oracle, season, **kw)
     assert st == 0
     runs = rows_to_runs(H.entries_as_runs(entries))
-    got = engine.vote(season.ts_ns, season.seg_offset, season.hash_duration_ns, engine.match_params(**kw), runs)
+    got = engine.vote(season.hash_duration_ns, engine.match_params(**kw), runs)
     assert got == want
     if kw["threshold"] >= 10:
         assert any(r[0] for r in want)
@@ -56,7 +51,7 @@ def test_vote_rejects_unsorted_runs(oracle):
     runs = rows_to_runs(rows[::-1])
     from needle_b200._lib import Nb200Error, ERR_INVALID_ARGUMENT
     with pytest.raises(Nb200Error) as e:
-        engine.vote(season.ts_ns, season.seg_offset, season.hash_duration_ns, engine.match_params(**kw), runs)
+        engine.vote(season.hash_duration_ns, engine.match_params(**kw), runs)
     assert e.value.status == ERR_INVALID_ARGUMENT
 
 
@@ -77,5 +72,5 @@ def test_heap_order_matters(oracle):
     st, want, entries = H.oracle_run(oracle, season, **kw)
     assert st == 0 and len(entries) >= 27
     runs = rows_to_runs(H.entries_as_runs(entries))
-    got = engine.vote(season.ts_ns, season.seg_offset, season.hash_duration_ns, engine.match_params(**kw), runs)
+    got = engine.vote(season.hash_duration_ns, engine.match_params(**kw), runs)
     assert got == want
