@@ -309,6 +309,7 @@ def run_b200(args):
         job.run_resident(pcmset)
     barrier()
     launches0 = ctx.last_kernel_ms()["n_launches"]
+    ctx.host_profile(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
     ev0.record()
@@ -322,6 +323,7 @@ def run_b200(args):
     sampler.active = False
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.last_kernel_ms()["n_launches"] - launches0
+    host_ms = {k: v / args.steps for k, v in ctx.host_profile(reset=True).items()}
     for k in kernel_ms:
         kernel_ms[k] /= args.steps
 
@@ -411,6 +413,7 @@ def run_b200(args):
         "clocks": clocks,
         "audio_hours_per_sec": hours_total / (step_ms * 1e-3),
         "kernel_ms_per_step": kernel_ms,
+        "host_phase_ms_per_step": host_ms,
         # the schema's roofline object, for the kernel with the largest share of the step
         "roofline": {
             "kernel": dominant, "bound": "hbm",

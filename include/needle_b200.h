@@ -80,6 +80,22 @@ int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
 enum { NB200_OPT_FORCE_GENERAL_MATCH = 1 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 
+/* Wall-clock milliseconds the library spent in each host-side phase (including
+ * the waits on the GPU inside it) since the last reset; for finding where a
+ * step's time goes beyond the kernels.  ms_out[NB200_HOST_PHASES]. */
+enum {
+    NB200_PHASE_PCM_UPLOAD = 0,   /* nb200_pcmset_upload: H2D (+ down-mix) */
+    NB200_PHASE_FP = 1,           /* nb200_fingerprint_run: K1 + K2 */
+    NB200_PHASE_LMIN = 2,         /* run-length bounds kernel + read-back */
+    NB200_PHASE_MATCH_SETUP = 3,  /* problem/tile tables built and uploaded */
+    NB200_PHASE_MATCH = 4,        /* K3 (+ retry) until the run count is known */
+    NB200_PHASE_SIMHASH = 5,      /* K4 + copy into the run set */
+    NB200_PHASE_RUNS_DOWNLOAD = 6,/* D2H of runs + sort */
+    NB200_PHASE_VOTE = 7,         /* heap replay + find_best_match */
+    NB200_HOST_PHASES = 8
+};
+int nb200_ctx_host_profile(nb200_ctx *ctx, double *ms_out, int reset);
+
 /* Pinned host memory (cudaHostAlloc) for PCM / hash staging. */
 int nb200_host_alloc(void **out, size_t bytes);
 int nb200_host_free(void *p);

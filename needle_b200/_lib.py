@@ -78,6 +78,7 @@ PROTOTYPES = {
     "nb200_ctx_destroy": (None, [_P]),
     "nb200_ctx_set_stream": (C.c_int, [_P, _P]),
     "nb200_ctx_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "nb200_ctx_host_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "nb200_ctx_synchronize": (C.c_int, [_P]),
     "nb200_ctx_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), _U64P]),
     "nb200_host_alloc": (C.c_int, [_PP, C.c_size_t]),

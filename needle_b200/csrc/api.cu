@@ -191,6 +191,15 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
     }
 }
 
+int nb200_ctx_host_profile(nb200_ctx *ctx, double *ms_out, int reset) {
+    if (!ctx) return NB200_ERR_NULL_ARGUMENT;
+    for (int k = 0; k < NB200_HOST_PHASES; k++) {
+        if (ms_out) ms_out[k] = ctx->host_ms[k];
+        if (reset) ctx->host_ms[k] = 0.0;
+    }
+    return NB200_OK;
+}
+
 int nb200_ctx_synchronize(nb200_ctx *ctx) {
     if (!ctx) return NB200_ERR_NULL_ARGUMENT;
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -457,6 +466,7 @@ int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *run
     if (rs->n_runs == 0) return NB200_OK;
     if (!runs_out) return NB200_ERR_NULL_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
+    PhaseTimer pt(ctx, NB200_PHASE_RUNS_DOWNLOAD);
     std::vector<DeviceRun> tmp(rs->n_runs);
     NB_CUDA(cudaMemcpyAsync(tmp.data(), rs->d_runs.p, rs->n_runs * sizeof(DeviceRun),
                             cudaMemcpyDeviceToHost, ctx->stream));
@@ -548,8 +558,10 @@ int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t
     NB_TRY(nb200_match_run(ctx, hs, nullptr, 0, params, &rs));
     std::vector<nb200_run> runs(std::max<uint64_t>(rs->n_runs, 1));
     int st = nb200_runset_download(ctx, rs, runs.data());
-    if (st == NB200_OK)
+    if (st == NB200_OK) {
+        PhaseTimer pt(ctx, NB200_PHASE_VOTE);
         st = vote_impl(hash_duration_ns, hs->n_videos, nullptr, 0, params, runs.data(), rs->n_runs, results);
+    }
     nb200_runset_free(rs);
     return st;
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
 #include <memory>
 #include <string>
 #include <vector>
@@ -148,6 +149,7 @@ struct nb200_ctx {
     cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
     bool ev_valid[4] = {false, false, false, false};
     uint64_t n_launches = 0;
+    double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
@@ -188,6 +190,18 @@ struct nb200_runset {
 };
 
 namespace nb200 {
+
+// Accumulates the wall time of a scope into ctx->host_ms[phase].
+struct PhaseTimer {
+    nb200_ctx *ctx;
+    int phase;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer(nb200_ctx *c, int p) : ctx(c), phase(p), t0(std::chrono::steady_clock::now()) {}
+    ~PhaseTimer() {
+        ctx->host_ms[phase] +=
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 // match.cu ---------------------------------------------------------------
 struct DeviceRun {

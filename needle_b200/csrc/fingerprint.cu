@@ -571,6 +571,7 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
     if (ps->n_segments % 2 != 0) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
     NB_TRY(ensure_fp_tables(ctx));
+    PhaseTimer pt(ctx, NB200_PHASE_FP);
 
     const uint32_t nseg = ps->n_segments;
     std::vector<FpSegment> segs(nseg);
@@ -710,6 +711,7 @@ int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_
     *out = nullptr;
     if (channels != 1 && channels != 2) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
+    PhaseTimer pt(ctx, NB200_PHASE_PCM_UPLOAD);
     nb200_pcmset *ps = new (std::nothrow) nb200_pcmset();
     if (!ps) return NB200_ERR_TOO_LARGE;
     ps->n_segments = n_segments;

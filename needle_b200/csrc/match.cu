@@ -31,6 +31,7 @@
 // pass the filter, so skipping them changes nothing.
 #include <algorithm>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "common.h"
@@ -595,6 +596,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
     const uint32_t nseg = 2 * hs->n_videos;
     std::vector<uint32_t> lmin(nseg, 1);
     if (nseg > 0 && hs->dev_total > 0) {
+        PhaseTimer pt(ctx, NB200_PHASE_LMIN);
         const size_t b_tab = (size_t)nseg * sizeof(SegTab), b_lmin = (size_t)nseg * sizeof(uint32_t);
         if (ctx->h_stage.reserve(b_tab + b_lmin) != NB200_OK || ctx->d_segtab.reserve(b_tab) != NB200_OK ||
             ctx->d_lmin.reserve(b_lmin) != NB200_OK)
@@ -630,6 +632,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
     }
     const bool fast = min_lcand >= 63 && !ctx->force_general_match;
 
+    std::unique_ptr<PhaseTimer> phase(new PhaseTimer(ctx, NB200_PHASE_MATCH_SETUP));
     auto rs = new nb200_runset();
     std::vector<MatchProblem> problems;
     problems.reserve(n_pairs * (endings ? 2 : 1));
@@ -726,6 +729,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
     if (ctx->d_runs.bytes / sizeof(DeviceRun) > run_cap)
         run_cap = (uint32_t)std::min<uint64_t>(ctx->d_runs.bytes / sizeof(DeviceRun), 0xffffffffull);
     unsigned int h_counters[4];
+    phase.reset(new PhaseTimer(ctx, NB200_PHASE_MATCH));
     for (int attempt = 0; attempt < 2; attempt++) {
         if (ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK) return fail(NB200_ERR_CUDA);
         NB_CUDA_F(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
@@ -761,6 +765,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         run_cap = h_counters[1];     // exact count is known now: rerun with room for all of them
     }
     rs->n_runs = h_counters[1];
+    phase.reset(new PhaseTimer(ctx, NB200_PHASE_SIMHASH));
     ctx->ev_valid[3] = false;
     if (rs->n_runs > 0) {
         const uint32_t nr = (uint32_t)rs->n_runs;

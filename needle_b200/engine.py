@@ -70,6 +70,14 @@ class Context:
     def set_option(self, option: int, value: int):
         check(lib().nb200_ctx_set_option(self._h, option, value), "nb200_ctx_set_option")
 
+    HOST_PHASES = ("pcm_upload", "fingerprint", "lmin", "match_setup", "match", "simhash", "runs_download", "vote")
+
+    def host_profile(self, reset: bool = True):
+        """Wall ms per host phase since the last reset (nb200_ctx_host_profile)."""
+        ms = (C.c_double * len(self.HOST_PHASES))()
+        check(lib().nb200_ctx_host_profile(self._h, ms, 1 if reset else 0), "nb200_ctx_host_profile")
+        return dict(zip(self.HOST_PHASES, list(ms)))
+
     def synchronize(self):
         check(lib().nb200_ctx_synchronize(self._h), "nb200_ctx_synchronize")
 

@@ -119,8 +119,9 @@ def test_fast_kernel_word_ownership(ctx, oracle):
     ts = synth.hash_timestamps(2 * n, 2)[:n]
     season = H.season_from_lists([(v, ts) for v in vids], [(np.zeros(0, np.uint32), np.zeros(0, np.uint64))] * 4)
     runs, _ = check_season(ctx, oracle, season, threshold=0)
-    assert len(runs) >= 15
-    check_season(ctx, oracle, season, threshold=0, min_opening_ns=16_000_000_000)    # lcand 66
+    assert len(runs) >= 2
+    runs, _ = check_season(ctx, oracle, season, threshold=0, min_opening_ns=16_000_000_000)    # lcand 66
+    assert len(runs) >= 6
 
 
 def test_threshold_extremes(ctx, oracle):
