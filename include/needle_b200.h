@@ -77,7 +77,11 @@ int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
 /* Tuning / test switches.  NB200_OPT_FORCE_GENERAL_MATCH (value 0|1): always run
  * the general match kernel, also where the fast variant (all candidate run
  * lengths >= 63 cells) would be chosen.  Results are identical either way. */
-enum { NB200_OPT_FORCE_GENERAL_MATCH = 1 };
+enum {
+    NB200_OPT_FORCE_GENERAL_MATCH = 1,
+    /* NB200_OPT_K1_VARIANT: 1 (default) = four warps per FFT frame, 0 = one warp per frame. */
+    NB200_OPT_K1_VARIANT = 2
+};
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 
 /* Wall-clock milliseconds the library spent in each host-side phase (including

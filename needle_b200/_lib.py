@@ -25,6 +25,7 @@ ERR_FORMAT = 8
 ERR_STATE = 9
 ERR_COMPARATOR_MINIMUM_PATHS = 10
 OPT_FORCE_GENERAL_MATCH = 1
+OPT_K1_VARIANT = 2
 
 
 class Nb200Error(RuntimeError):

@@ -24,7 +24,7 @@ HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"),
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-Wall,-Wextra,-fno-fast-math,-ffp-contract=off",
+    "-Xcompiler", "-fPIC,-Wall,-Wextra,-fno-fast-math,-ffp-contract=off,-mpopcnt",
     "--fmad=true", "-Xptxas", "-v",
 ]
 

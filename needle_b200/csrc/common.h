@@ -158,6 +158,8 @@ struct nb200_ctx {
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
+    nb200::DevBuf d_g4_twa, d_g4_twb, d_g4_base, d_g4_notes;
+    int k1_variant = 1;   // 0: warp per frame, 1: four warps per frame
     nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
 

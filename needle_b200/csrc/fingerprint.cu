@@ -357,6 +357,208 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
     }
 }
 
+// ---------------------------------------------------------------------------
+// K1, four-warps-per-frame variant ("g4").  The warp-per-frame kernel above keeps
+// 64 complex values per lane: 255 registers, 8 warps per SM, and ptxas has no
+// room to overlap dependent packed ops (ncu: issue active 49 %, stall "wait" 1.0).
+// Here a frame belongs to a GROUP of 128 threads holding 16 complex values each
+// (~64 registers -> 32 warps per SM), 2048 = 16 x 16 x 8:
+//   n = 128 a + 8 b + c,  k = ka + 16 kb + 256 kc
+//   pass A  thread r = 8b+c: 16-point FFT over a, twiddle W_2048^(r ka)   -> E1[ka][r]
+//   pass B  thread (ka, c):  16-point FFT over b, twiddle W_128^(c kb)    -> E2[ka + 16 kb][c]
+//   pass C  thread j: residues q = j and 256 - j, 8-point FFT over c each -> Z[q + 256 kc]
+// The partner bin Z[2048 - k] of the split step has residue 256 - q: it is in
+// the SAME thread, so the split needs no exchange at all, and
+// |X[2048-k]|^2 = |E - W O|^2 comes for free next to |X[k]|^2 = |E + W O|^2.
+// Two transposes through shared memory (named barriers per group), chroma
+// fold by per-thread accumulators in shared memory.
+constexpr int G4_THREADS = 128;
+constexpr int G4_GROUPS = 8;                      // frames in flight per CTA
+constexpr int G4_E1_STRIDE = 136;                 // float2 row stride of E1 (16 rows), conflict-free both ways
+constexpr int G4_E2_STRIDE = 9;                   // float2 row stride of E2 (256 rows)
+constexpr int G4_E_ELEMS = 256 * G4_E2_STRIDE;    // 2304 >= 16 * 136
+constexpr int G4_TWB_STRIDE = 17;
+constexpr int G4_SMEM_BYTES = (FP_HALF + 16 * G4_THREADS + 8 * G4_TWB_STRIDE + G4_GROUPS * G4_E_ELEMS) * 8;
+constexpr int G4_SLOTS = 11;                      // bins per thread that fall into [10, 1308)
+
+__constant__ float2 c_w16[16], c_w16r[16];        // exp(-2 pi i e / 16) and its (-y, x) form
+
+// 16-point FFT, n = n1 + 4 n2, k = 4 k1 + k2: X[4 k1 + k2] ends up at v[k1 + 4 k2].
+__device__ __forceinline__ void fft16(f2 *v) {
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++) fft4<4>(v + n1);
+#pragma unroll
+    for (int n1 = 1; n1 < 4; n1++)
+#pragma unroll
+        for (int k2 = 1; k2 < 4; k2++)
+            v[n1 + 4 * k2] = cmulc(v[n1 + 4 * k2], c_w16[n1 * k2], c_w16r[n1 * k2]);
+#pragma unroll
+    for (int k2 = 0; k2 < 4; k2++) fft4<1>(v + 4 * k2);
+}
+__device__ __forceinline__ constexpr int pos16(int k) { return (k >> 2) + 4 * (k & 3); }
+
+struct G4Args {
+    const int16_t *pcm;
+    const FpSegment *segs;
+    uint32_t n_segs;
+    uint32_t total_frames;
+    const float2 *window;    // [2048]
+    const float2 *tw_a;      // [16][128] W_2048^(r ka)
+    const float2 *tw_b;      // [8][17]   W_128^(c kb)
+    const float2 *base;      // [128][2]  W_4096^(q1), W_4096^(q2) of thread j
+    const uint2 *notes;      // [128]     11 x 4-bit pitch classes of thread j's bins (12 = unused)
+    float *chroma;
+};
+
+__device__ __forceinline__ void group_sync(int group) {
+    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G4_THREADS) : "memory");
+}
+
+__device__ __forceinline__ const int16_t *frame_src_g4(const G4Args &a, uint32_t frame) {
+    uint32_t lo = 0, hi = a.n_segs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.segs[mid].frame_begin <= frame) lo = mid; else hi = mid;
+    }
+    return a.pcm + a.segs[lo].pcm_off + (uint64_t)(frame - a.segs[lo].frame_begin) * FP_HOP;
+}
+
+__device__ __forceinline__ float power2(f2 x) { return fmaf(x.x, x.x, x.y * x.y); }
+
+__global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_kernel(const G4Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    f2 *s_window = reinterpret_cast<f2 *>(smem_raw);          // 2048
+    f2 *s_twa = s_window + FP_HALF;                           // 16 * 128
+    f2 *s_twb = s_twa + 16 * G4_THREADS;                      // 8 * 17
+    f2 *s_e_all = s_twb + 8 * G4_TWB_STRIDE;                  // G4_GROUPS * G4_E_ELEMS
+
+    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
+        s_window[i] = a.window[i];
+        s_twa[i] = a.tw_a[i];
+    }
+    if (threadIdx.x < 8 * G4_TWB_STRIDE) s_twb[threadIdx.x] = a.tw_b[threadIdx.x];
+    __syncthreads();
+
+    const int group = threadIdx.x >> 7;
+    const int r = threadIdx.x & (G4_THREADS - 1);
+    const int lane = threadIdx.x & 31;
+    const int wig = r >> 5;                                   // warp in group
+    f2 *E = s_e_all + group * G4_E_ELEMS;
+    float *acc = reinterpret_cast<float *>(E);                // [13][128], aliases E between pass C and the next frame
+    const int ka_b = r >> 3, c_b = r & 7;                     // pass B role
+    const int q1 = r == 0 ? 0 : r, q2 = r == 0 ? 128 : 256 - r;   // pass C role
+    const f2 base1 = a.base[2 * r], base2 = a.base[2 * r + 1];
+    const uint2 notes = a.notes[r];
+
+    const uint32_t n_blocks = (a.total_frames + G4_GROUPS - 1) / G4_GROUPS;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t frame = blk * G4_GROUPS + group;
+        if (frame >= a.total_frames) break;                   // uniform per group; only group barriers below
+        const int16_t *src = frame_src_g4(a, frame);
+
+        f2 v[16];
+        // ---- pass A: z[128 a + r], window fused, 16-point FFT over a
+        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + r;
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = mul2(s16x2_to_float(__ldg(p + 128 * i)), s_window[128 * i + r]);
+        } else {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(src - 1) + r;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t w0 = __ldg(p + 128 * i), w1 = __ldg(p + 128 * i + 1);
+                v[i] = mul2(s16x2_to_float(__funnelshift_r(w0, w1, 16)), s_window[128 * i + r]);
+            }
+        }
+        fft16(v);
+        E[r] = v[0];
+#pragma unroll
+        for (int ka = 1; ka < 16; ka++) E[ka * G4_E1_STRIDE + r] = cmul(v[pos16(ka)], s_twa[ka * G4_THREADS + r]);
+        group_sync(group);
+
+        // ---- pass B: thread (ka, c), 16-point FFT over b
+#pragma unroll
+        for (int b = 0; b < 16; b++) v[b] = E[ka_b * G4_E1_STRIDE + 8 * b + c_b];
+        group_sync(group);
+        fft16(v);
+        E[G4_E2_STRIDE * ka_b + c_b] = v[0];
+#pragma unroll
+        for (int kb = 1; kb < 16; kb++)
+            E[G4_E2_STRIDE * (ka_b + 16 * kb) + c_b] = cmul(v[pos16(kb)], s_twb[c_b * G4_TWB_STRIDE + kb]);
+        group_sync(group);
+
+        // ---- pass C: residues q1, q2 = 256 - q1 (thread 0: 0 and 128), 8-point FFT over c
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            v[c] = E[G4_E2_STRIDE * q1 + c];
+            v[8 + c] = E[G4_E2_STRIDE * q2 + c];
+        }
+        group_sync(group);
+#pragma unroll
+        for (int n = 0; n < 13; n++) acc[n * G4_THREADS + r] = 0.f;
+        fft8<1>(v);
+        fft8<1>(v + 8);
+        // now Z[q1 + 256 kc] = v[kc], Z[q2 + 256 kc] = v[8 + kc]
+
+        // ---- split + power + chroma fold
+        if (r != 0) {
+            // k = q1 + 256 kc pairs with 2048 - k = q2 + 256 (7 - kc)
+#pragma unroll
+            for (int kc = 0; kc < 8; kc++) {
+                const f2 z = v[kc], zp = v[8 + 7 - kc];
+                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);               // 2E
+                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));     // 2O
+                const f2 w = cmulc(base1, c_w16[kc], c_w16r[kc]);               // W_4096^(q1 + 256 kc)
+                const f2 t = cmul(o, w);
+                if (kc <= 5) {                                                  // bin k: slot kc
+                    const uint32_t note = ((kc < 8 ? notes.x : notes.y) >> (4 * (kc & 7))) & 15u;
+                    acc[note * G4_THREADS + r] += power2(add2(e, t));
+                }
+                if (kc >= 3) {                                                  // bin 2048 - k: slot 6 + (kc - 3)
+                    const int s = 6 + kc - 3;
+                    const uint32_t note = ((s < 8 ? notes.x : notes.y) >> (4 * (s & 7))) & 15u;
+                    acc[note * G4_THREADS + r] += power2(sub2(e, t));
+                }
+            }
+        } else {
+            // residue 0: k = 256 kc pairs with 256 (8 - kc) inside v[0..8); slots 0..4 <-> kc = 1..5
+#pragma unroll
+            for (int kc = 1; kc <= 5; kc++) {
+                const f2 z = v[kc], zp = v[(8 - kc) & 7];
+                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+                const f2 t = cmulc(o, c_w16[kc], c_w16r[kc]);                   // W_4096^(256 kc) = W_16^kc
+                const uint32_t note = (notes.x >> (4 * (kc - 1))) & 15u;
+                acc[note * G4_THREADS + r] += power2(add2(e, t));
+            }
+            // residue 128: k = 128 + 256 kc pairs with 128 + 256 (7 - kc) inside v[8..16); slots 5..9 <-> kc = 0..4
+#pragma unroll
+            for (int kc = 0; kc <= 4; kc++) {
+                const f2 z = v[8 + kc], zp = v[8 + 7 - kc];
+                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+                const f2 w = cmulc(base2, c_w16[kc], c_w16r[kc]);               // W_4096^(128 + 256 kc)
+                const f2 t = cmul(o, w);
+                const int s = 5 + kc;
+                const uint32_t note = ((s < 8 ? notes.x : notes.y) >> (4 * (s & 7))) & 15u;
+                acc[note * G4_THREADS + r] += power2(add2(e, t));
+            }
+        }
+        group_sync(group);
+        // ---- reduce: warp w of the group sums pitch classes 3w .. 3w+2 over the 128 threads
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const int n = 3 * wig + i;
+            float s = (acc[n * G4_THREADS + lane] + acc[n * G4_THREADS + 32 + lane]) +
+                      (acc[n * G4_THREADS + 64 + lane] + acc[n * G4_THREADS + 96 + lane]);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) a.chroma[(uint64_t)frame * FP_BANDS + n] = 0.25f * s;
+        }
+        group_sync(group);   // acc is about to be overwritten by the next frame's E1
+    }
+}
+
 // --------------------------------------------------------------------- K2
 
 struct K2Args {
@@ -551,6 +753,61 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpyToSymbol(c_w64r, rot(w64).data(), sizeof(float2) * 64));
     NB_CUDA(cudaMemcpyToSymbol(c_w32r, rot(w32).data(), sizeof(float2) * 32));
     NB_CUDA(cudaMemcpyToSymbol(c_w128r, rot(w128).data(), sizeof(float2) * FP_T));
+    {
+        std::vector<float2> w16(16);
+        for (int e = 0; e < 16; e++) w16[e] = make_float2((float)cos(-2.0 * PI * e / 16), (float)sin(-2.0 * PI * e / 16));
+        NB_CUDA(cudaMemcpyToSymbol(c_w16, w16.data(), sizeof(float2) * 16));
+        NB_CUDA(cudaMemcpyToSymbol(c_w16r, rot(w16).data(), sizeof(float2) * 16));
+    }
+    {
+        // tables of the four-warps-per-frame kernel
+        std::vector<float2> twa(16 * G4_THREADS), twb(8 * G4_TWB_STRIDE, make_float2(1.f, 0.f)), base(2 * G4_THREADS);
+        std::vector<uint2> notes4(G4_THREADS);
+        for (int ka = 0; ka < 16; ka++)
+            for (int r = 0; r < G4_THREADS; r++) {
+                const double ang = -2.0 * PI * (double)(r * ka) / FP_HALF;
+                twa[ka * G4_THREADS + r] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        for (int c = 0; c < 8; c++)
+            for (int kb = 0; kb < 16; kb++) {
+                const double ang = -2.0 * PI * (double)(c * kb) / 128.0;
+                twb[c * G4_TWB_STRIDE + kb] = make_float2((float)cos(ang), (float)sin(ang));
+            }
+        auto note_of = [&](int k) -> uint32_t {
+            if (k < min_index || k >= max_index) return 12u;
+            const double freq = (double)k * FP_SAMPLE_RATE / FP_FRAME;
+            const double octave = log(freq / (440.0 / 16.0)) / log(2.0);
+            return (uint32_t)(int)(FP_BANDS * (octave - floor(octave)));
+        };
+        for (int j = 0; j < G4_THREADS; j++) {
+            const int q1 = j == 0 ? 0 : j, q2 = j == 0 ? 128 : 256 - j;
+            base[2 * j] = make_float2((float)cos(-2.0 * PI * q1 / FP_FRAME), (float)sin(-2.0 * PI * q1 / FP_FRAME));
+            base[2 * j + 1] = make_float2((float)cos(-2.0 * PI * q2 / FP_FRAME), (float)sin(-2.0 * PI * q2 / FP_FRAME));
+            uint64_t bits = 0;
+            for (int s2 = 0; s2 < 16; s2++) {
+                int k = -1;
+                if (j != 0) {
+                    if (s2 <= 5) k = q1 + 256 * s2;                       // bin k, kc = s2
+                    else if (s2 <= 10) k = FP_HALF - (q1 + 256 * (s2 - 3));   // bin 2048 - k, kc = s2 - 3
+                } else {
+                    if (s2 <= 4) k = 256 * (s2 + 1);                      // residue 0, kc = s2 + 1
+                    else if (s2 <= 9) k = 128 + 256 * (s2 - 5);           // residue 128, kc = s2 - 5
+                }
+                bits |= (uint64_t)(k < 0 ? 12u : note_of(k)) << (4 * s2);
+            }
+            notes4[j] = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
+        }
+        NB_TRY(ctx->d_g4_twa.alloc(sizeof(float2) * twa.size()));
+        NB_TRY(ctx->d_g4_twb.alloc(sizeof(float2) * twb.size()));
+        NB_TRY(ctx->d_g4_base.alloc(sizeof(float2) * base.size()));
+        NB_TRY(ctx->d_g4_notes.alloc(sizeof(uint2) * notes4.size()));
+        NB_CUDA(cudaMemcpy(ctx->d_g4_twa.p, twa.data(), sizeof(float2) * twa.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaMemcpy(ctx->d_g4_twb.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaMemcpy(ctx->d_g4_base.p, base.data(), sizeof(float2) * base.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaMemcpy(ctx->d_g4_notes.p, notes4.data(), sizeof(uint2) * notes4.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     G4_SMEM_BYTES));
+    }
     NB_CUDA(cudaMemcpyToSymbol(c_cls, cls, sizeof(cls)));
     NB_CUDA(cudaMemcpyToSymbol(c_fir, FP_FIR_COEFFS, sizeof(double) * FP_FIR_LEN));
     NB_TRY(ctx->d_fp_window.alloc(sizeof(float2) * FP_HALF));
@@ -656,6 +913,20 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
         const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, n_blocks);
         const size_t smem = K1_SMEM_BYTES;
         NB_CUDA_F(cudaEventRecord(ctx->ev[0], st));
+        if (ctx->k1_variant == 1) {
+            G4Args g;
+            g.pcm = k1.pcm;
+            g.segs = k1.segs;
+            g.n_segs = nseg;
+            g.total_frames = (uint32_t)frames;
+            g.window = k1.window;
+            g.tw_a = ctx->d_g4_twa.as<float2>();
+            g.tw_b = ctx->d_g4_twb.as<float2>();
+            g.base = ctx->d_g4_base.as<float2>();
+            g.notes = ctx->d_g4_notes.as<uint2>();
+            g.chroma = k1.chroma;
+            fp_fft_chroma_g4_kernel<<<grid1, G4_GROUPS * G4_THREADS, G4_SMEM_BYTES, st>>>(g);
+        } else
         fp_fft_chroma_kernel<<<grid1, FP_WARPS * 32, smem, st>>>(k1);
         NB_CUDA_F(cudaGetLastError());
         NB_CUDA_F(cudaEventRecord(ctx->ev[1], st));

@@ -150,10 +150,17 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
         }
         const size_t nc = cand.size();
         // |distinct_matches[i]| = #{ j : popcount(h_i ^ h_j) < T + T/2 }; i is a key iff that is > 0
+        // (the relation is symmetric: visit each unordered pair once)
         std::vector<uint32_t> cluster(nc, 0);
-        for (size_t i = 0; i < nc; i++)
-            for (size_t j = 0; j < nc; j++)
-                if ((uint32_t)__builtin_popcount(cand[i].match_hash ^ cand[j].match_hash) < bias) cluster[i]++;
+        for (size_t i = 0; i < nc; i++) {
+            const uint32_t hi = cand[i].match_hash;
+            if (0u < bias) cluster[i]++;   // i with itself: distance 0
+            for (size_t j = i + 1; j < nc; j++)
+                if ((uint32_t)__builtin_popcount(hi ^ cand[j].match_hash) < bias) {
+                    cluster[i]++;
+                    cluster[j]++;
+                }
+        }
 
         nb200_search_result &res = results[v];
         res.present = 1;

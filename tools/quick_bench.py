@@ -33,17 +33,21 @@ for e in range(28):
 t0 = time.perf_counter()
 ps = engine.PcmSet.upload(ctx, segs)
 t1 = time.perf_counter()
-for _ in range(3):
-    hs = ps.fingerprint()
-ts = []
-for _ in range(5):
-    t2 = time.perf_counter(); hs = ps.fingerprint(); t3 = time.perf_counter()
-    ms = ctx.last_kernel_ms()
-    ts.append((ms["fp_fft_chroma"], ms["fp_classify"], (t3 - t2) * 1e3))
 frames = sum(synth.num_frames(s.size) for s in segs)
-k1 = min(t[0] for t in ts)
-out["fingerprint_28x20min"] = dict(frames=frames, audio_hours=sum(s.size for s in segs) / 11025 / 3600,
-                                   upload_ms=(t1 - t0) * 1e3, k1_ms=k1, k2_ms=min(t[1] for t in ts),
-                                   wall_ms=min(t[2] for t in ts), Mframes_per_s=frames / k1 / 1e3,
-                                   fp32_TFLOPs=frames * 134.6e3 / (k1 * 1e-3) / 1e12)
+for variant in (1, 0):
+    ctx.set_option(2, variant)
+    for _ in range(3):
+        hs = ps.fingerprint()
+    ts = []
+    for _ in range(5):
+        t2 = time.perf_counter(); hs = ps.fingerprint(); t3 = time.perf_counter()
+        ms = ctx.last_kernel_ms()
+        ts.append((ms["fp_fft_chroma"], ms["fp_classify"], (t3 - t2) * 1e3))
+    k1 = min(t[0] for t in ts)
+    out["fingerprint_28x20min_k1v%d" % variant] = dict(
+        frames=frames, audio_hours=sum(s.size for s in segs) / 11025 / 3600,
+        upload_ms=(t1 - t0) * 1e3, k1_ms=k1, k2_ms=min(t[1] for t in ts),
+        wall_ms=min(t[2] for t in ts), Mframes_per_s=frames / k1 / 1e3,
+        fp32_TFLOPs=frames * 134.6e3 / (k1 * 1e-3) / 1e12)
+ctx.set_option(2, 1)
 print(json.dumps(out, indent=1))
