@@ -79,7 +79,8 @@ int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
  * lengths >= 63 cells) would be chosen.  Results are identical either way. */
 enum {
     NB200_OPT_FORCE_GENERAL_MATCH = 1,
-    /* NB200_OPT_K1_VARIANT: 1 (default) = four warps per FFT frame, 0 = one warp per frame. */
+    /* NB200_OPT_K1_VARIANT: 0 = one warp per FFT frame; 4, 5, 6 = four warps per frame with
+     * that many frames in flight per CTA.  Same results; a tuning switch. */
     NB200_OPT_K1_VARIANT = 2
 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);

@@ -151,6 +151,8 @@ int nb200_ctx_create(int device, nb200_ctx **out) {
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < 8; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+    for (int k = 0; ok && k < 8; k++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && ctx->h_small.reserve(256) == NB200_OK;
     if (!ok) {
         set_last_error("nb200_ctx_create", cudaGetLastError());
@@ -166,8 +168,10 @@ void nb200_ctx_destroy(nb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    for (int k = 0; k < 8; k++)
+    for (int k = 0; k < 8; k++) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+        if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -187,7 +191,7 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
         ctx->force_general_match = value != 0;
         return NB200_OK;
     case NB200_OPT_K1_VARIANT:
-        if (value != 0 && value != 1) return NB200_ERR_INVALID_ARGUMENT;
+        if (value != 0 && (value < 4 || value > 6)) return NB200_ERR_INVALID_ARGUMENT;
         ctx->k1_variant = (int)value;
         return NB200_OK;
     default:

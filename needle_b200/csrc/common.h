@@ -147,6 +147,7 @@ struct nb200_ctx {
     cudaStream_t stream = nullptr;     // the one in use (own or caller's)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
+    cudaEvent_t ev_chunk[8] = {};      // H2D chunk landed (pipelined analyze)
     bool ev_valid[4] = {false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
@@ -159,7 +160,7 @@ struct nb200_ctx {
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
     nb200::DevBuf d_g4_twa, d_g4_twb, d_g4_base, d_g4_notes;
-    int k1_variant = 1;   // 0: warp per frame, 1: four warps per frame
+    int k1_variant = 0;   // 0: one warp per frame; 4/5/6: four warps per frame, that many frames per CTA
     nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
 

@@ -200,7 +200,7 @@ struct K1Args {
     const int16_t *pcm;
     const FpSegment *segs;
     uint32_t n_segs;
-    uint32_t total_frames;
+    uint32_t frame_begin, frame_end;   // this launch covers global frames [begin, end)
     const float2 *window;    // [2048]  (w[2n], w[2n+1]) / 32767
     const float2 *twiddle;   // [32][64] W_2048^(n2 k1)
     const float2 *lane_w;    // [32] W_4096^L
@@ -246,13 +246,13 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
     const int partner = (32 - lane) & 31;
     const f2 lane_w = a.lane_w[lane];
 
-    const uint32_t n_blocks = (a.total_frames + FP_WARPS - 1) / FP_WARPS;
+    const uint32_t n_blocks = (a.frame_end - a.frame_begin + FP_WARPS - 1) / FP_WARPS;
     uint32_t blk = blockIdx.x;
-    uint32_t frame = blk * FP_WARPS + warp;
+    uint32_t frame = a.frame_begin + blk * FP_WARPS + warp;
     uint32_t phase = 0;
     // misalignment (bytes, even, < 16) of the frame that is in flight / resident
     uint32_t delta = 0;
-    if (blk < n_blocks && frame < a.total_frames) {
+    if (blk < n_blocks && frame < a.frame_end) {
         const int16_t *src = frame_src(a, frame);
         delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
         if (lane == 0) {
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
     }
 
     for (; blk < n_blocks; blk += gridDim.x) {
-        frame = blk * FP_WARPS + warp;
-        if (frame >= a.total_frames) break;   // warp-uniform; only warp-level sync below
+        frame = a.frame_begin + blk * FP_WARPS + warp;
+        if (frame >= a.frame_end) break;   // warp-uniform; only warp-level sync below
 
         f2 v[64];
         // ---- PCM (landed by the bulk copy) -> registers, window fused:
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
         // ---- the exchange buffer is free: start the next frame's PCM on its way
         {
             const uint32_t nblk = blk + gridDim.x;
-            const uint32_t nframe = nblk * FP_WARPS + warp;
-            if (nblk < n_blocks && nframe < a.total_frames) {
+            const uint32_t nframe = a.frame_begin + nblk * FP_WARPS + warp;
+            if (nblk < n_blocks && nframe < a.frame_end) {
                 const int16_t *src = frame_src(a, nframe);
                 delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
                 fence_proxy_async();   // our generic reads of xchg are ordered before the async write
@@ -373,13 +373,10 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
 // Two transposes through shared memory (named barriers per group), chroma
 // fold by per-thread accumulators in shared memory.
 constexpr int G4_THREADS = 128;
-constexpr int G4_GROUPS = 8;                      // frames in flight per CTA
 constexpr int G4_E1_STRIDE = 136;                 // float2 row stride of E1 (16 rows), conflict-free both ways
-constexpr int G4_E2_STRIDE = 9;                   // float2 row stride of E2 (256 rows)
-constexpr int G4_E_ELEMS = 256 * G4_E2_STRIDE;    // 2304 >= 16 * 136
+constexpr int G4_E_ELEMS = 16 * G4_E1_STRIDE;     // 2176 >= 2048 (E2: 256 rows of 8, XOR-swizzled)
 constexpr int G4_TWB_STRIDE = 17;
-constexpr int G4_SMEM_BYTES = (FP_HALF + 16 * G4_THREADS + 8 * G4_TWB_STRIDE + G4_GROUPS * G4_E_ELEMS) * 8;
-constexpr int G4_SLOTS = 11;                      // bins per thread that fall into [10, 1308)
+constexpr int g4_smem_bytes(int groups) { return (FP_HALF + 8 * G4_TWB_STRIDE + groups * G4_E_ELEMS) * 8; }
 
 __constant__ float2 c_w16[16], c_w16r[16];        // exp(-2 pi i e / 16) and its (-y, x) form
 
@@ -401,7 +398,7 @@ struct G4Args {
     const int16_t *pcm;
     const FpSegment *segs;
     uint32_t n_segs;
-    uint32_t total_frames;
+    uint32_t frame_begin, frame_end;
     const float2 *window;    // [2048]
     const float2 *tw_a;      // [16][128] W_2048^(r ka)
     const float2 *tw_b;      // [8][17]   W_128^(c kb)
@@ -409,6 +406,10 @@ struct G4Args {
     const uint2 *notes;      // [128]     11 x 4-bit pitch classes of thread j's bins (12 = unused)
     float *chroma;
 };
+
+// E2[q][c] lives at 8 q + (c ^ ((q >> 1) & 7)): writers (two consecutive ka x eight c per
+// half-warp) and readers (sixteen consecutive q, one c) both hit 16 distinct 8-byte banks.
+__device__ __forceinline__ int e2_index(int q, int c) { return 8 * q + (c ^ ((q >> 1) & 7)); }
 
 __device__ __forceinline__ void group_sync(int group) {
     asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G4_THREADS) : "memory");
@@ -425,17 +426,15 @@ __device__ __forceinline__ const int16_t *frame_src_g4(const G4Args &a, uint32_t
 
 __device__ __forceinline__ float power2(f2 x) { return fmaf(x.x, x.x, x.y * x.y); }
 
+// G4_GROUPS = frames in flight per CTA: 4 -> 128 registers per thread, 5 -> 102, 6 -> 85
+template <int G4_GROUPS>
 __global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_kernel(const G4Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     f2 *s_window = reinterpret_cast<f2 *>(smem_raw);          // 2048
-    f2 *s_twa = s_window + FP_HALF;                           // 16 * 128
-    f2 *s_twb = s_twa + 16 * G4_THREADS;                      // 8 * 17
+    f2 *s_twb = s_window + FP_HALF;                           // 8 * 17
     f2 *s_e_all = s_twb + 8 * G4_TWB_STRIDE;                  // G4_GROUPS * G4_E_ELEMS
 
-    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
-        s_window[i] = a.window[i];
-        s_twa[i] = a.tw_a[i];
-    }
+    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) s_window[i] = a.window[i];
     if (threadIdx.x < 8 * G4_TWB_STRIDE) s_twb[threadIdx.x] = a.tw_b[threadIdx.x];
     __syncthreads();
 
@@ -449,11 +448,15 @@ __global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_ker
     const int q1 = r == 0 ? 0 : r, q2 = r == 0 ? 128 : 256 - r;   // pass C role
     const f2 base1 = a.base[2 * r], base2 = a.base[2 * r + 1];
     const uint2 notes = a.notes[r];
+    // pass-A twiddles W_2048^(r ka), ka = 1..15: thread constants, kept in registers for all frames
+    f2 twa[15];
+#pragma unroll
+    for (int ka = 1; ka < 16; ka++) twa[ka - 1] = a.tw_a[ka * G4_THREADS + r];
 
-    const uint32_t n_blocks = (a.total_frames + G4_GROUPS - 1) / G4_GROUPS;
+    const uint32_t n_blocks = (a.frame_end - a.frame_begin + G4_GROUPS - 1) / G4_GROUPS;
     for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const uint32_t frame = blk * G4_GROUPS + group;
-        if (frame >= a.total_frames) break;                   // uniform per group; only group barriers below
+        const uint32_t frame = a.frame_begin + blk * G4_GROUPS + group;
+        if (frame >= a.frame_end) break;                      // uniform per group; only group barriers below
         const int16_t *src = frame_src_g4(a, frame);
 
         f2 v[16];
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_ker
         fft16(v);
         E[r] = v[0];
 #pragma unroll
-        for (int ka = 1; ka < 16; ka++) E[ka * G4_E1_STRIDE + r] = cmul(v[pos16(ka)], s_twa[ka * G4_THREADS + r]);
+        for (int ka = 1; ka < 16; ka++) E[ka * G4_E1_STRIDE + r] = cmul(v[pos16(ka)], twa[ka - 1]);
         group_sync(group);
 
         // ---- pass B: thread (ka, c), 16-point FFT over b
@@ -481,17 +484,17 @@ __global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_ker
         for (int b = 0; b < 16; b++) v[b] = E[ka_b * G4_E1_STRIDE + 8 * b + c_b];
         group_sync(group);
         fft16(v);
-        E[G4_E2_STRIDE * ka_b + c_b] = v[0];
+        E[e2_index(ka_b, c_b)] = v[0];
 #pragma unroll
         for (int kb = 1; kb < 16; kb++)
-            E[G4_E2_STRIDE * (ka_b + 16 * kb) + c_b] = cmul(v[pos16(kb)], s_twb[c_b * G4_TWB_STRIDE + kb]);
+            E[e2_index(ka_b + 16 * kb, c_b)] = cmul(v[pos16(kb)], s_twb[c_b * G4_TWB_STRIDE + kb]);
         group_sync(group);
 
         // ---- pass C: residues q1, q2 = 256 - q1 (thread 0: 0 and 128), 8-point FFT over c
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            v[c] = E[G4_E2_STRIDE * q1 + c];
-            v[8 + c] = E[G4_E2_STRIDE * q2 + c];
+            v[c] = E[e2_index(q1, c)];
+            v[8 + c] = E[e2_index(q2, c)];
         }
         group_sync(group);
 #pragma unroll
@@ -805,8 +808,12 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
         NB_CUDA(cudaMemcpy(ctx->d_g4_twb.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice));
         NB_CUDA(cudaMemcpy(ctx->d_g4_base.p, base.data(), sizeof(float2) * base.size(), cudaMemcpyHostToDevice));
         NB_CUDA(cudaMemcpy(ctx->d_g4_notes.p, notes4.data(), sizeof(uint2) * notes4.size(), cudaMemcpyHostToDevice));
-        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     G4_SMEM_BYTES));
+        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     g4_smem_bytes(4)));
+        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     g4_smem_bytes(5)));
+        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     g4_smem_bytes(6)));
     }
     NB_CUDA(cudaMemcpyToSymbol(c_cls, cls, sizeof(cls)));
     NB_CUDA(cudaMemcpyToSymbol(c_fir, FP_FIR_COEFFS, sizeof(double) * FP_FIR_LEN));
@@ -822,8 +829,12 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     return NB200_OK;
 }
 
-int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
-                         uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out) {
+// host_pcm != NULL: the PCM is not in ps->d_pcm yet.  It is copied there in chunks of
+// segments on the copy stream while K1 already runs on the chunks that have landed
+// (H2D over PCIe is ~10 ms for a season, K1 ~1.5 ms: everything but the last chunk hides).
+static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, const int16_t *const *host_pcm,
+                                     uint32_t stride, uint64_t delay_ns, uint64_t item_ns,
+                                     const uint64_t *seek_to_ns, nb200_hashset **out) {
     if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;   // Rust's step_by(0) panics
     if (ps->n_segments % 2 != 0) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -904,34 +915,79 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
         k1.pcm = ps->d_pcm.as<int16_t>();
         k1.segs = ctx->d_fp_desc.as<FpSegment>();
         k1.n_segs = nseg;
-        k1.total_frames = (uint32_t)frames;
         k1.window = ctx->d_fp_window.as<float2>();
         k1.twiddle = ctx->d_fp_twiddle.as<float2>();
         k1.lane_w = ctx->d_fp_lane.as<float2>();
         k1.chroma = ctx->d_chroma.as<float>();
-        const uint32_t n_blocks = (uint32_t)((frames + FP_WARPS - 1) / FP_WARPS);
-        const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, n_blocks);
-        const size_t smem = K1_SMEM_BYTES;
+        G4Args g;
+        g.pcm = k1.pcm;
+        g.segs = k1.segs;
+        g.n_segs = nseg;
+        g.window = k1.window;
+        g.tw_a = ctx->d_g4_twa.as<float2>();
+        g.tw_b = ctx->d_g4_twb.as<float2>();
+        g.base = ctx->d_g4_base.as<float2>();
+        g.notes = ctx->d_g4_notes.as<uint2>();
+        g.chroma = k1.chroma;
+        // K1 over global frames [f0, f1)
+        auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
+            if (f1 <= f0) return cudaSuccess;
+            const uint32_t nf = f1 - f0;
+            if (ctx->k1_variant >= 4) {
+                const int groups = ctx->k1_variant;
+                g.frame_begin = f0;
+                g.frame_end = f1;
+                const uint32_t ggrid = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + groups - 1) / groups);
+                if (groups == 4)
+                    fp_fft_chroma_g4_kernel<4><<<ggrid, 4 * G4_THREADS, g4_smem_bytes(4), st>>>(g);
+                else if (groups == 5)
+                    fp_fft_chroma_g4_kernel<5><<<ggrid, 5 * G4_THREADS, g4_smem_bytes(5), st>>>(g);
+                else
+                    fp_fft_chroma_g4_kernel<6><<<ggrid, 6 * G4_THREADS, g4_smem_bytes(6), st>>>(g);
+            } else {
+                k1.frame_begin = f0;
+                k1.frame_end = f1;
+                const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + FP_WARPS - 1) / FP_WARPS);
+                fp_fft_chroma_kernel<<<grid1, FP_WARPS * 32, K1_SMEM_BYTES, st>>>(k1);
+            }
+            ctx->n_launches++;
+            return cudaGetLastError();
+        };
         NB_CUDA_F(cudaEventRecord(ctx->ev[0], st));
-        if (ctx->k1_variant == 1) {
-            G4Args g;
-            g.pcm = k1.pcm;
-            g.segs = k1.segs;
-            g.n_segs = nseg;
-            g.total_frames = (uint32_t)frames;
-            g.window = k1.window;
-            g.tw_a = ctx->d_g4_twa.as<float2>();
-            g.tw_b = ctx->d_g4_twb.as<float2>();
-            g.base = ctx->d_g4_base.as<float2>();
-            g.notes = ctx->d_g4_notes.as<uint2>();
-            g.chroma = k1.chroma;
-            fp_fft_chroma_g4_kernel<<<grid1, G4_GROUPS * G4_THREADS, G4_SMEM_BYTES, st>>>(g);
-        } else
-        fp_fft_chroma_kernel<<<grid1, FP_WARPS * 32, smem, st>>>(k1);
-        NB_CUDA_F(cudaGetLastError());
+        if (!host_pcm) {
+            NB_CUDA_F(launch_k1(0, (uint32_t)frames));
+        } else {
+            // the copy stream must not overtake earlier work on the compute stream that
+            // may still read the (pooled) PCM buffer
+            NB_CUDA_F(cudaEventRecord(ctx->ev_chunk[7], st));
+            NB_CUDA_F(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[7], 0));
+            // chunks of consecutive segments, ~equal bytes
+            constexpr int N_CHUNKS = 6;
+            uint64_t total_mono = 0;
+            for (uint32_t s2 = 0; s2 < nseg; s2++) total_mono += ps->n_mono[s2];
+            uint32_t seg = 0;
+            uint64_t done = 0;
+            for (int c = 0; c < N_CHUNKS && seg < nseg; c++) {
+                const uint64_t target = total_mono * (uint64_t)(c + 1) / N_CHUNKS;
+                const uint32_t first = seg;
+                while (seg < nseg && (done < target || c == N_CHUNKS - 1)) {
+                    if (ps->n_mono[seg] > 0)
+                        NB_CUDA_F(cudaMemcpyAsync(ps->d_pcm.as<int16_t>() + ps->dev_offset[seg], host_pcm[seg],
+                                                  ps->n_mono[seg] * sizeof(int16_t), cudaMemcpyHostToDevice,
+                                                  ctx->copy_stream));
+                    done += ps->n_mono[seg];
+                    seg++;
+                }
+                if (seg == first) continue;
+                NB_CUDA_F(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+                NB_CUDA_F(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
+                const uint32_t f0 = segs[first].frame_begin;
+                const uint32_t f1 = segs[seg - 1].frame_begin + segs[seg - 1].n_frames;
+                NB_CUDA_F(launch_k1(f0, f1));
+            }
+        }
         NB_CUDA_F(cudaEventRecord(ctx->ev[1], st));
         ctx->ev_valid[0] = true;
-        ctx->n_launches++;
 
         if (tiles > 0) {
             K2Args k2;
@@ -959,6 +1015,11 @@ int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride
     return NB200_OK;
 }
 
+int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
+                         uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out) {
+    return fingerprint_run_pipelined(ctx, ps, nullptr, stride, delay_ns, item_ns, seek_to_ns, out);
+}
+
 }  // namespace nb200
 
 using namespace nb200;
@@ -976,8 +1037,9 @@ extern "C" {
 
 uint64_t nb200_num_raw_hashes(uint64_t n_mono_samples) { return num_raw(n_mono_samples); }
 
-int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
-                        int channels, uint32_t n_segments, nb200_pcmset **out) {
+// copy == false: only lay the set out and allocate it (the caller streams the PCM in itself)
+static int pcmset_make(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                       int channels, uint32_t n_segments, bool copy, nb200_pcmset **out) {
     if (!ctx || !out || (n_segments && (!pcm || !n_samples_total))) return NB200_ERR_NULL_ARGUMENT;
     *out = nullptr;
     if (channels != 1 && channels != 2) return NB200_ERR_INVALID_ARGUMENT;
@@ -1010,7 +1072,7 @@ int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_
     cudaError_t e;
     if (channels == 2 && ctx->d_stereo.reserve((size_t)max_seg * sizeof(int16_t)) != NB200_OK)
         return fail(NB200_ERR_CUDA, nullptr, cudaSuccess);
-    for (uint32_t s = 0; s < n_segments; s++) {
+    for (uint32_t s = 0; copy && s < n_segments; s++) {
         if (ps->n_mono[s] == 0) continue;
         int16_t *dst = ps->d_pcm.as<int16_t>() + ps->dev_offset[s];
         if (channels == 1) {
@@ -1031,6 +1093,11 @@ int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_
     if (e != cudaSuccess) return fail(NB200_ERR_CUDA, "cudaStreamSynchronize", e);
     *out = ps;
     return NB200_OK;
+}
+
+int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
+                        int channels, uint32_t n_segments, nb200_pcmset **out) {
+    return pcmset_make(ctx, pcm, n_samples_total, channels, n_segments, true, out);
 }
 
 void nb200_pcmset_free(nb200_pcmset *ps) { delete ps; }
@@ -1186,10 +1253,19 @@ int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64
     const uint64_t stride = (hash_duration_ns / 1000000ull) / NB200_ITEM_DURATION_MS;
     if (stride == 0 || stride > 0xffffffffull) return NB200_ERR_INVALID_ARGUMENT;
     nb200_pcmset *ps = nullptr;
-    NB_TRY(nb200_pcmset_upload(ctx, pcm, n_samples_total, channels, 2 * n_videos, &ps));
     nb200_hashset *hs = nullptr;
-    int st = fingerprint_run_impl(ctx, ps, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
+    int st;
+    if (channels == 1) {
+        // mono: stream the PCM in chunk by chunk underneath K1
+        NB_TRY(pcmset_make(ctx, pcm, n_samples_total, channels, 2 * n_videos, false, &ps));
+        NB_TRY(ensure_fp_tables(ctx));
+        st = fingerprint_run_pipelined(ctx, ps, pcm, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
+                                       NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs);
+    } else {
+        NB_TRY(nb200_pcmset_upload(ctx, pcm, n_samples_total, channels, 2 * n_videos, &ps));
+        st = fingerprint_run_impl(ctx, ps, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
                                   NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs);
+    }
     nb200_pcmset_free(ps);
     if (st != NB200_OK) return st;
     std::vector<uint64_t> hd(n_videos, hash_duration_ns);

@@ -8,6 +8,8 @@ from needle_b200 import engine, synth
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 ctx = engine.Context(0)
+if len(sys.argv) > 2:
+    ctx.set_option(2, int(sys.argv[2]))     # NB200_OPT_K1_VARIANT
 rng = np.random.default_rng(0)
 n = 20 * 60 * 11025
 segs = []
