@@ -291,7 +291,7 @@ def run_b200(args):
         _rs.free()
         _hs.free()
     else:
-        _season = backend.season_from_gathered(job._buffers()[1], job.plan)   # filled by the run above
+        _season = backend.season_from_gathered(job._buffers(), job.plan, world)   # filled by the run above
         n_runs_local = backend.match(_season, params, my_pairs).shape[0]
         _season.free()
     d2h_bytes = 24 * n_runs_local + 16 + (8 * int(sl.sum()) if rank == 0 else 0)

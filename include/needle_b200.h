@@ -213,6 +213,14 @@ int nb200_hashset_from_device(nb200_ctx *ctx, const void *d_hashes, const void *
 int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
                                         const uint64_t *src_hash_off, const uint64_t *src_ts_off,
                                         const uint64_t *seg_len, uint32_t n_videos, nb200_hashset **out);
+/* A season that lives in caller-owned device memory, not copied: segment s has
+ * seg_len[s] elements starting at element dev_offset[s] of BOTH arrays (offsets
+ * multiples of 4).  The memory must stay valid while the set is in use.  This is
+ * how the multi-GPU flow matches straight out of the all-gather receive
+ * buffers (one for hashes, one for timestamps, rank-major, equal capacity). */
+int nb200_hashset_view(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                       const uint64_t *dev_offset, const uint64_t *seg_len, uint32_t n_videos,
+                       nb200_hashset **out);
 void nb200_hashset_free(nb200_hashset *hs);
 
 /* Launch the match kernels for the given pairs (NULL = all i<j); returns once
@@ -250,6 +258,18 @@ void nb200_pcmset_free(nb200_pcmset *ps);
 int nb200_fingerprint_run(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride,
                           uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
                           nb200_hashset **out);
+
+/* Same, writing into caller-owned device arrays (capacity elements each: u32
+ * hashes, u64 timestamps) in the library's device layout -- every segment
+ * starts at the next multiple of 4 elements, in segment order.  dev_offset_out
+ * [n_segments] and seg_len_out[n_segments] (may be NULL) receive that layout;
+ * nb200_fingerprint_layout computes it without running anything.  With the
+ * arrays being all-gather send buffers, fingerprints go to the wire without a copy. */
+int nb200_fingerprint_layout(const uint64_t *n_mono_samples, uint32_t n_segments, uint32_t stride,
+                             uint64_t *dev_offset_out, uint64_t *seg_len_out, uint64_t *total_out);
+int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride,
+                               uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
+                               void *d_hashes_out, void *d_ts_ns_out, uint64_t capacity);
 
 /* One-shot with host buffers: raw sub-fingerprints (stride 1, no timestamps)
  * of each segment == chromaprint_get_raw_fingerprint.  out_hashes[k] is

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "nb200_hashset_device_ptrs": (C.c_int, [_P, _PP, _PP]),
     "nb200_hashset_from_device": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _PP]),
     "nb200_hashset_from_device_scattered": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint32, _PP]),
+    "nb200_hashset_view": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, _PP]),
     "nb200_hashset_free": (None, [_P]),
     "nb200_match_run": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), _PP]),
     "nb200_runset_count": (C.c_int, [_P, _U64P, _U64P]),
@@ -109,6 +110,8 @@ PROTOTYPES = {
     "nb200_pcmset_upload": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, _PP]),
     "nb200_pcmset_free": (None, [_P]),
     "nb200_fingerprint_run": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _PP]),
+    "nb200_fingerprint_layout": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _U64P]),
+    "nb200_fingerprint_run_into": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P, C.c_uint64]),
     "nb200_fingerprint_batch": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P]),
     "nb200_fp_new": (C.c_int, [_P, _PP]),
     "nb200_fp_free": (None, [_P]),

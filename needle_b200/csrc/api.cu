@@ -451,6 +451,42 @@ int nb200_hashset_from_device_scattered(nb200_ctx *ctx, const void *d_hashes, co
     return NB200_OK;
 }
 
+int nb200_hashset_view(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns,
+                       const uint64_t *dev_offset, const uint64_t *seg_len, uint32_t n_videos,
+                       nb200_hashset **out) {
+    if (!ctx || !dev_offset || !seg_len || !out) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    const uint32_t nseg = 2 * n_videos;
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    hs->n_videos = n_videos;
+    hs->seg_offset.assign(nseg + 1, 0);
+    hs->dev_offset.resize(nseg);
+    hs->seg_len.resize(nseg);
+    uint64_t extent = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+        if ((dev_offset[s] & 3) || dev_offset[s] + seg_len[s] > 0xfffffff0ull || seg_len[s] > 0x7fffff00ull) {
+            delete hs;
+            return NB200_ERR_INVALID_ARGUMENT;
+        }
+        hs->dev_offset[s] = (uint32_t)dev_offset[s];
+        hs->seg_len[s] = (uint32_t)seg_len[s];
+        hs->seg_offset[s + 1] = hs->seg_offset[s] + seg_len[s];
+        extent = std::max<uint64_t>(extent, dev_offset[s] + seg_len[s]);
+    }
+    hs->total = hs->seg_offset[nseg];
+    hs->dev_total = extent;
+    if (hs->total > 0 && (!d_hashes || !d_ts_ns)) {
+        delete hs;
+        return NB200_ERR_NULL_ARGUMENT;
+    }
+    hs->d_hashes.borrow(const_cast<void *>(d_hashes), extent * sizeof(uint32_t));
+    hs->d_ts.borrow(const_cast<void *>(d_ts_ns), extent * sizeof(uint64_t));
+    hs->sorted_layout = false;
+    *out = hs;
+    return NB200_OK;
+}
+
 void nb200_hashset_free(nb200_hashset *hs) { delete hs; }
 
 /* ------------------------------------------------------------------- match */
@@ -475,10 +511,13 @@ int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *run
     if (!runs_out) return NB200_ERR_NULL_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
     PhaseTimer pt(ctx, NB200_PHASE_RUNS_DOWNLOAD);
-    std::vector<DeviceRun> tmp(rs->n_runs);
-    NB_CUDA(cudaMemcpyAsync(tmp.data(), rs->d_runs.p, rs->n_runs * sizeof(DeviceRun),
+    // through pinned staging: a pageable destination makes the copy synchronous and slow
+    NB_TRY(ctx->h_runs.reserve(rs->n_runs * sizeof(DeviceRun)));
+    NB_CUDA(cudaMemcpyAsync(ctx->h_runs.p, rs->d_runs.p, rs->n_runs * sizeof(DeviceRun),
                             cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DeviceRun *tmp_begin = ctx->h_runs.as<DeviceRun>();
+    std::vector<DeviceRun> tmp(tmp_begin, tmp_begin + rs->n_runs);
     // the reference's push order: pair, opening before ending, i desc, j desc
     // (problems are numbered in (pair, is_ending) order)
     std::sort(tmp.begin(), tmp.end(), [](const DeviceRun &a, const DeviceRun &b) {

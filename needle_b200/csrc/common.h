@@ -80,6 +80,13 @@ struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     std::shared_ptr<DevPool> pool;
+    bool borrowed = false;   // points into memory owned by the caller
+    void borrow(void *q, size_t n) {
+        release();
+        p = q;
+        bytes = n;
+        borrowed = true;
+    }
     int alloc(size_t n, const std::shared_ptr<DevPool> &from = nullptr) {
         release();
         if (n == 0) n = 16;
@@ -103,11 +110,12 @@ struct DevBuf {
         return alloc(n + n / 4);
     }
     void release() {
-        if (p) {
+        if (p && !borrowed) {
             if (pool) pool->put(p, bytes); else cudaFree(p);
         }
         p = nullptr;
         bytes = 0;
+        borrowed = false;
         pool.reset();
     }
     ~DevBuf() { release(); }
@@ -155,7 +163,7 @@ struct nb200_ctx {
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
-    nb200::PinnedBuf h_stage, h_small;
+    nb200::PinnedBuf h_stage, h_small, h_runs;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
@@ -174,6 +182,7 @@ struct nb200_hashset {
     uint64_t total = 0;                 // packed element count
     uint64_t dev_total = 0;             // aligned element count
     nb200::DevBuf d_hashes, d_ts;
+    bool sorted_layout = true;          // dev_offset ascending with the segment index (false for views)
 };
 
 struct nb200_pcmset {

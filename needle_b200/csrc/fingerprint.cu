@@ -832,9 +832,13 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
 // host_pcm != NULL: the PCM is not in ps->d_pcm yet.  It is copied there in chunks of
 // segments on the copy stream while K1 already runs on the chunks that have landed
 // (H2D over PCIe is ~10 ms for a season, K1 ~1.5 ms: everything but the last chunk hides).
+// ext_hashes / ext_ts != NULL: write into these caller-owned device arrays
+// (ext_capacity elements) instead of allocating; the returned set borrows them.
 static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, const int16_t *const *host_pcm,
                                      uint32_t stride, uint64_t delay_ns, uint64_t item_ns,
-                                     const uint64_t *seek_to_ns, nb200_hashset **out) {
+                                     const uint64_t *seek_to_ns, nb200_hashset **out,
+                                     void *ext_hashes = nullptr, void *ext_ts = nullptr,
+                                     uint64_t ext_capacity = 0) {
     if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;   // Rust's step_by(0) panics
     if (ps->n_segments % 2 != 0) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -886,8 +890,12 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         hs->total = seg_offset[nseg];
         hs->dev_total = dev;
     }
-    if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
-        hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK)
+    if (ext_hashes) {
+        if (hs->dev_total > ext_capacity) return fail(NB200_ERR_TOO_LARGE);
+        hs->d_hashes.borrow(ext_hashes, (size_t)ext_capacity * sizeof(uint32_t));
+        hs->d_ts.borrow(ext_ts, (size_t)ext_capacity * sizeof(uint64_t));
+    } else if (hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
+               hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK)
         return fail(NB200_ERR_CUDA);
     cudaStream_t st = ctx->stream;
 #define NB_CUDA_F(expr)                      \
@@ -1107,6 +1115,32 @@ int nb200_fingerprint_run(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t strid
     if (!ctx || !ps || !out) return NB200_ERR_NULL_ARGUMENT;
     *out = nullptr;
     return fingerprint_run_impl(ctx, ps, stride, delay_ns, item_ns, seek_to_ns, out);
+}
+
+int nb200_fingerprint_layout(const uint64_t *n_mono_samples, uint32_t n_segments, uint32_t stride,
+                             uint64_t *dev_offset_out, uint64_t *seg_len_out, uint64_t *total_out) {
+    if (!n_mono_samples && n_segments) return NB200_ERR_NULL_ARGUMENT;
+    if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;
+    uint64_t dev = 0;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        const uint64_t len = (num_raw(n_mono_samples[s]) + stride - 1) / stride;
+        if (dev_offset_out) dev_offset_out[s] = dev;
+        if (seg_len_out) seg_len_out[s] = len;
+        dev += (len + 3) & ~3ull;
+    }
+    if (total_out) *total_out = dev;
+    return NB200_OK;
+}
+
+int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride,
+                               uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
+                               void *d_hashes_out, void *d_ts_ns_out, uint64_t capacity) {
+    if (!ctx || !ps || !d_hashes_out || !d_ts_ns_out) return NB200_ERR_NULL_ARGUMENT;
+    nb200_hashset *hs = nullptr;
+    NB_TRY(fingerprint_run_pipelined(ctx, ps, nullptr, stride, delay_ns, item_ns, seek_to_ns, &hs,
+                                     d_hashes_out, d_ts_ns_out, capacity));
+    nb200_hashset_free(hs);   // borrowed arrays: nothing is released
+    return NB200_OK;
 }
 
 int nb200_fingerprint_batch(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,

@@ -545,23 +545,17 @@ struct SegTab {
     uint32_t dev_offset, len;
 };
 __global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *__restrict__ segs,
-                                uint32_t n_seg, uint64_t dev_total, uint64_t min_open_ns, uint64_t min_end_ns,
-                                uint32_t *__restrict__ lmin) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= dev_total) return;
-    uint32_t lo = 0, hi = n_seg;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (segs[mid].dev_offset <= idx) lo = mid; else hi = mid;
-    }
-    const SegTab sg = segs[lo];
-    const uint32_t i = (uint32_t)(idx - sg.dev_offset);
+                                uint64_t min_open_ns, uint64_t min_end_ns, uint32_t *__restrict__ lmin) {
+    // blockIdx.y = segment (any placement in memory), blockIdx.x * blockDim.x + threadIdx.x = element
+    const uint32_t seg = blockIdx.y;
+    const SegTab sg = segs[seg];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sg.len || i == 0) return;
     const uint64_t *t = ts + sg.dev_offset;
-    const uint64_t mn = (lo & 1) ? min_end_ns : min_open_ns;
+    const uint64_t mn = (seg & 1) ? min_end_ns : min_open_ns;
     const uint64_t ti = t[i];
     if (ti < t[i - 1]) {
-        atomicMin(&lmin[lo], 1u);
+        atomicMin(&lmin[seg], 1u);
         return;
     }
     if (ti < mn || t[0] > ti - mn) return;          // no start is far enough from i
@@ -573,7 +567,7 @@ __global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *_
         if (t[mid] <= limit) a = mid; else b = mid;
     }
     const uint32_t len = i - a;
-    atomicMin(&lmin[lo], len < 1u ? 1u : len);
+    atomicMin(&lmin[seg], len < 1u ? 1u : len);
 }
 
 // ------------------------------------------------------------------- host
@@ -611,9 +605,11 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         }
         NB_CUDA(cudaMemcpyAsync(ctx->d_segtab.p, tab, b_tab, cudaMemcpyHostToDevice, s));
         NB_CUDA(cudaMemcpyAsync(ctx->d_lmin.p, init, b_lmin, cudaMemcpyHostToDevice, s));
-        seg_lmin_kernel<<<(unsigned)((hs->dev_total + 255) / 256), 256, 0, s>>>(
-            hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), nseg, hs->dev_total, params->min_opening_ns,
-            params->min_ending_ns, ctx->d_lmin.as<uint32_t>());
+        uint32_t max_len = 1;
+        for (uint32_t k = 0; k < nseg; k++) max_len = std::max(max_len, hs->seg_len[k]);
+        seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
+            hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), params->min_opening_ns, params->min_ending_ns,
+            ctx->d_lmin.as<uint32_t>());
         NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
         NB_CUDA(cudaMemcpyAsync(init, ctx->d_lmin.p, b_lmin, cudaMemcpyDeviceToHost, s));

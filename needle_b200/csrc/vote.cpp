@@ -43,38 +43,44 @@ float as_secs_f32(uint64_t ns) {
     return s + f;
 }
 
-// ComparatorHeapEntry, fields in declaration order so that std::tuple's
-// lexicographic operator< equals the derived Ord (comparator.rs:20-35).
-using Entry = std::tuple<uint64_t,                       // score
-                         uint64_t, uint64_t,             // src_longest_run
-                         uint64_t, uint64_t,             // dst_longest_run
-                         uint32_t, uint32_t,             // src/dst_match_hash
-                         bool, bool, bool, bool,         // is_src_opening, is_src_ending, is_dst_..
-                         uint64_t, uint64_t>;            // src/dst_hash_duration
+// ComparatorHeapEntry (comparator.rs:20-35).  The derived Ord is lexicographic over
+// the fields in declaration order: score, src_longest_run, dst_longest_run,
+// src_match_hash, dst_match_hash, the four is_* flags, the two hash durations.
+// Within one heap (one table of one pair) the flags and hash durations are the
+// same for every entry, so they never decide a comparison.
+struct Entry {
+    uint64_t score, src_start, src_end, dst_start, dst_end;
+    uint32_t src_hash, dst_hash;
+};
 
-// BinaryHeap::push: append then sift the new element up while it is greater
-// than its parent.
-void heap_push(std::vector<Entry> &heap, const Entry &e) {
+inline bool entry_greater(const Entry &a, const Entry &b) {
+    if (a.score != b.score) return a.score > b.score;
+    if (a.src_start != b.src_start) return a.src_start > b.src_start;
+    if (a.src_end != b.src_end) return a.src_end > b.src_end;
+    if (a.dst_start != b.dst_start) return a.dst_start > b.dst_start;
+    if (a.dst_end != b.dst_end) return a.dst_end > b.dst_end;
+    if (a.src_hash != b.src_hash) return a.src_hash > b.src_hash;
+    return a.dst_hash > b.dst_hash;
+}
+
+// BinaryHeap::push on heap[base..): append, then sift the new element up while it
+// is greater than its parent.
+void heap_push(std::vector<Entry> &heap, size_t base, const Entry &e) {
     heap.push_back(e);
-    size_t pos = heap.size() - 1;
+    size_t pos = heap.size() - 1 - base;
     while (pos > 0) {
         const size_t parent = (pos - 1) / 2;
-        if (!(e > heap[parent])) break;
-        heap[pos] = heap[parent];
+        if (!entry_greater(e, heap[base + parent])) break;
+        heap[base + pos] = heap[base + parent];
         pos = parent;
     }
-    heap[pos] = e;
+    heap[base + pos] = e;
 }
 
 struct Candidate {
     uint64_t start, end, hash_duration;
     uint32_t match_hash;
     bool is_opening;
-};
-
-struct PairInfo {            // OpeningAndEndingInfo; src_* and dst_* lists hold the same entries
-    std::vector<Entry> openings, endings;
-    bool empty() const { return openings.empty() && endings.empty(); }
 };
 
 }  // namespace
@@ -90,76 +96,93 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
     }
     std::memset(results, 0, sizeof(nb200_search_result) * n_videos);
 
-    // rebuild every pair's heap arrays from the runs (already in push order)
-    std::vector<PairInfo> infos(n_pairs);
-    for (uint64_t r = 0; r < n_runs; r++) {
-        const nb200_run &run = runs[r];
-        if (run.pair >= n_pairs) return NB200_ERR_INVALID_ARGUMENT;
-        if (r > 0) {   // (pair, is_ending, i desc, j desc)
-            const nb200_run &q = runs[r - 1];
-            auto key = [](const nb200_run &x) {
-                return std::make_tuple(x.pair, x.is_ending, ~x.i_end, ~x.j_end);
-            };
-            if (!(key(q) < key(run))) return NB200_ERR_INVALID_ARGUMENT;
+    // Replay every table's heap from its runs (already in push order).  All heaps live
+    // back to back in one array; group g = 2 * pair + is_ending covers
+    // heap[group_begin[g] .. group_begin[g + 1]).
+    std::vector<Entry> heap;
+    heap.reserve(n_runs);
+    std::vector<uint64_t> group_begin(2 * n_pairs + 1, 0);
+    {
+        uint64_t g_prev = 0;
+        for (uint64_t r = 0; r < n_runs; r++) {
+            const nb200_run &run = runs[r];
+            if (run.pair >= n_pairs || run.is_ending > 1) return NB200_ERR_INVALID_ARGUMENT;
+            if (pairs[run.pair][0] >= n_videos || pairs[run.pair][1] >= n_videos) return NB200_ERR_INVALID_ARGUMENT;
+            if (r > 0) {   // (pair, is_ending, i desc, j desc)
+                const nb200_run &q = runs[r - 1];
+                auto key = [](const nb200_run &x) {
+                    return std::make_tuple(x.pair, x.is_ending, ~x.i_end, ~x.j_end);
+                };
+                if (!(key(q) < key(run))) return NB200_ERR_INVALID_ARGUMENT;
+            }
+            const uint64_t g = 2ull * run.pair + run.is_ending;
+            for (uint64_t k = g_prev + 1; k <= g; k++) group_begin[k] = heap.size();
+            g_prev = g;
+            const Entry e = {run.len, run.src_start_ns, run.src_end_ns, run.dst_start_ns, run.dst_end_ns,
+                             run.src_simhash, run.dst_simhash};
+            heap_push(heap, (size_t)group_begin[g], e);
         }
-        const uint32_t src = pairs[run.pair][0], dst = pairs[run.pair][1];
-        if (src >= n_videos || dst >= n_videos) return NB200_ERR_INVALID_ARGUMENT;
-        const bool is_opening = !run.is_ending;
-        Entry en(run.len, run.src_start_ns, run.src_end_ns, run.dst_start_ns, run.dst_end_ns,
-                 run.src_simhash, run.dst_simhash, is_opening, !is_opening, is_opening, !is_opening,
-                 hash_duration_ns[src], hash_duration_ns[dst]);
-        heap_push(run.is_ending ? infos[run.pair].endings : infos[run.pair].openings, en);
+        for (uint64_t k = g_prev + 1; k <= 2 * n_pairs; k++) group_begin[k] = heap.size();
     }
 
-    // info_map: only non-empty infos, in pair order (:562, :580-588)
-    std::vector<std::vector<std::pair<const PairInfo *, bool>>> info_map(n_videos);
-    for (uint64_t k = 0; k < n_pairs; k++) {
-        if (infos[k].empty()) continue;
-        info_map[pairs[k][0]].push_back({&infos[k], true});
-        info_map[pairs[k][1]].push_back({&infos[k], false});
+    // info_map: for every video the non-empty pair infos it takes part in, in pair
+    // order, with whether it is the source (:562, :580-588).  Counting sort by video.
+    std::vector<uint64_t> vid_begin(n_videos + 1, 0);
+    auto pair_nonempty = [&](uint64_t k) { return group_begin[2 * k + 2] > group_begin[2 * k]; };
+    for (uint64_t k = 0; k < n_pairs; k++)
+        if (pair_nonempty(k)) {
+            vid_begin[pairs[k][0] + 1]++;
+            vid_begin[pairs[k][1] + 1]++;
+        }
+    for (uint32_t v = 0; v < n_videos; v++) vid_begin[v + 1] += vid_begin[v];
+    std::vector<uint64_t> vid_pairs(vid_begin[n_videos]);   // 2 * pair + is_source
+    {
+        std::vector<uint64_t> cursor(vid_begin.begin(), vid_begin.end() - 1);
+        for (uint64_t k = 0; k < n_pairs; k++)
+            if (pair_nonempty(k)) {
+                // a pair (v, v) cannot come from the reference's pair list, but keep its order: source first
+                vid_pairs[cursor[pairs[k][0]]++] = 2 * k + 1;
+                vid_pairs[cursor[pairs[k][1]]++] = 2 * k;
+            }
     }
 
     int status = NB200_OK;
     const uint32_t T = params->hash_match_threshold;
     const uint32_t bias = T + T / 2;
+    std::vector<Candidate> cand;
+    std::vector<uint32_t> cluster;
     for (uint32_t v = 0; v < n_videos; v++) {
-        const auto &matches = info_map[v];
-        if (matches.empty()) continue;   // find_best_match -> None
-        std::vector<Candidate> cand;
-        for (const auto &mi : matches) {
-            const PairInfo *m = mi.first;
-            const bool is_source = mi.second;
-            for (int pass = 0; pass < 2; pass++) {
-                for (const Entry &e : (pass == 0 ? m->openings : m->endings)) {
+        if (vid_begin[v + 1] == vid_begin[v]) continue;   // find_best_match -> None
+        cand.clear();
+        for (uint64_t m = vid_begin[v]; m < vid_begin[v + 1]; m++) {
+            const uint64_t k = vid_pairs[m] >> 1;
+            const bool is_source = vid_pairs[m] & 1;
+            const uint64_t hd = hash_duration_ns[is_source ? pairs[k][0] : pairs[k][1]];
+            for (int e = 0; e < 2; e++)   // openings, then endings (:413-431)
+                for (uint64_t x = group_begin[2 * k + e]; x < group_begin[2 * k + e + 1]; x++) {
+                    const Entry &en = heap[x];
                     Candidate c;
-                    if (is_source) {
-                        c.start = std::get<1>(e);
-                        c.end = std::get<2>(e);
-                        c.hash_duration = std::get<11>(e);
-                        c.match_hash = std::get<5>(e);
-                    } else {
-                        c.start = std::get<3>(e);
-                        c.end = std::get<4>(e);
-                        c.hash_duration = std::get<12>(e);
-                        c.match_hash = std::get<6>(e);
-                    }
-                    c.is_opening = pass == 0;
+                    c.start = is_source ? en.src_start : en.dst_start;
+                    c.end = is_source ? en.src_end : en.dst_end;
+                    c.match_hash = is_source ? en.src_hash : en.dst_hash;
+                    c.hash_duration = hd;
+                    c.is_opening = e == 0;
                     cand.push_back(c);
                 }
-            }
         }
         const size_t nc = cand.size();
         // |distinct_matches[i]| = #{ j : popcount(h_i ^ h_j) < T + T/2 }; i is a key iff that is > 0
         // (the relation is symmetric: visit each unordered pair once)
-        std::vector<uint32_t> cluster(nc, 0);
+        cluster.assign(nc, bias > 0 ? 1u : 0u);   // i with itself: distance 0
         for (size_t i = 0; i < nc; i++) {
             const uint32_t hi = cand[i].match_hash;
-            if (0u < bias) cluster[i]++;   // i with itself: distance 0
-            for (size_t j = i + 1; j < nc; j++)
-                if ((uint32_t)__builtin_popcount(hi ^ cand[j].match_hash) < bias) {
-                    cluster[i]++;
-                    cluster[j]++;
-                }
+            uint32_t mine = 0;
+            for (size_t j = i + 1; j < nc; j++) {
+                const uint32_t hit = (uint32_t)__builtin_popcount(hi ^ cand[j].match_hash) < bias ? 1u : 0u;
+                mine += hit;
+                cluster[j] += hit;
+            }
+            cluster[i] += mine;
         }
 
         nb200_search_result &res = results[v];

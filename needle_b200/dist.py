@@ -68,19 +68,33 @@ def shard_pairs(seg_len: np.ndarray, pairs: np.ndarray, world: int, include_endi
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world)]
 
 
+def device_layout(n_mono, stride: int):
+    """The library's device layout of a list of segments (nb200_fingerprint_layout):
+    every segment starts at the next multiple of 4 elements.  -> (offsets, lengths, total)"""
+    off, ln, pos = [], [], 0
+    for x in n_mono:
+        n = stored_hashes(int(x), stride)
+        off.append(pos)
+        ln.append(n)
+        pos += (n + 3) & ~3
+    return off, ln, pos
+
+
 @dataclass
 class SeasonPlan:
-    """Who fingerprints what, and where each segment lands in the all-gather
-    receive buffer.  Per-rank block = [u32 hashes x cap | u64 ts x cap] bytes."""
+    """Who fingerprints what, and where each segment sits in the all-gather
+    receive buffers.  Two buffers, rank-major, `cap` elements per rank: u32
+    hashes and u64 timestamps, each rank's block in the library's own device
+    layout -- so K2 writes straight into the send buffers and the match kernel
+    reads straight out of the receive buffers (nb200_hashset_view): the
+    exchange adds no copy kernel on either side."""
     world: int
     n_videos: int
     stride: int
     videos_of_rank: list          # list[list[int]]
     seg_len: np.ndarray           # u64 [2N] stored hashes per segment (opening_k, ending_k)
-    cap: int                      # hashes per rank block (even)
-    block_bytes: int
-    src_hash_off: np.ndarray      # u64 [2N] element offset in the receive buffer viewed as u32
-    src_ts_off: np.ndarray        # u64 [2N] element offset in the receive buffer viewed as u64
+    cap: int                      # elements per rank block (multiple of 4)
+    dev_offset: np.ndarray        # u64 [2N] element offset of each segment in the receive buffers
 
     @staticmethod
     def build(n_mono_per_segment, world: int, stride: int = 2) -> "SeasonPlan":
@@ -90,21 +104,16 @@ class SeasonPlan:
         seg_len = np.array([stored_hashes(int(x), stride) for x in n_mono], dtype=np.uint64)
         costs = n_mono[0::2] + n_mono[1::2]
         vor = shard_videos(costs, world)
-        per_rank = [int(sum(int(seg_len[2 * v]) + int(seg_len[2 * v + 1]) for v in vs)) for vs in vor]
-        cap = max(per_rank + [2])
-        cap += cap & 1
-        block_bytes = 12 * cap
-        src_h = np.zeros(2 * n_videos, np.uint64)
-        src_t = np.zeros(2 * n_videos, np.uint64)
-        for r, vs in enumerate(vor):
-            local = 0
-            for v in vs:
-                for e in (0, 1):
-                    s = 2 * v + e
-                    src_h[s] = (r * block_bytes) // 4 + local
-                    src_t[s] = (r * block_bytes + 4 * cap) // 8 + local
-                    local += int(seg_len[s])
-        return SeasonPlan(world, n_videos, stride, vor, seg_len, cap, block_bytes, src_h, src_t)
+        layouts = []
+        for vs in vor:
+            segs = [2 * v + e for v in vs for e in (0, 1)]
+            layouts.append((segs,) + device_layout([n_mono[s] for s in segs], stride))
+        cap = max([total for _s, _o, _l, total in layouts] + [4])
+        dev_offset = np.zeros(2 * n_videos, np.uint64)
+        for r, (segs, off, _ln, _total) in enumerate(layouts):
+            for s, o in zip(segs, off):
+                dev_offset[s] = r * cap + o
+        return SeasonPlan(world, n_videos, stride, vor, seg_len, cap, dev_offset)
 
     def local_segments(self, rank: int) -> list[int]:
         """Global segment ids this rank fingerprints, in its local order."""
@@ -135,15 +144,11 @@ class GpuBackend:
         torch.cuda.set_device(self.device)
         self.ctx = engine.Context(device_index)
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._run_bufs = None
+        self._cnt_bufs = None
 
     def upload_pcm(self, segments):
         return self.engine.PcmSet.upload(self.ctx, segments)
-
-    def fingerprint_into(self, pcmset, plan: SeasonPlan, seek_to_ns, send):
-        """K1/K2 on this rank's segments, packed into the send block (uint8 tensor)."""
-        hs = pcmset.fingerprint(stride=plan.stride, seek_to_ns=seek_to_ns)
-        hs.export_packed(send.data_ptr(), send.data_ptr() + 4 * plan.cap)
-        hs.free()
 
     def fingerprint_search(self, pcmset, plan: SeasonPlan, seek_to_ns, hash_duration_ns, params):
         """Single-GPU path: nb200_fingerprint_run + nb200_search_hashset."""
@@ -153,9 +158,26 @@ class GpuBackend:
         finally:
             hs.free()
 
-    def season_from_gathered(self, recv, plan: SeasonPlan):
-        return self.engine.HashSet.from_device_scattered(self.ctx, recv.data_ptr(), recv.data_ptr(),
-                                                         plan.src_hash_off, plan.src_ts_off, plan.seg_len)
+    def alloc_exchange(self, plan: SeasonPlan):
+        t = self.torch
+        return {"hash_send": t.zeros(plan.cap, dtype=t.int32, device=self.device),
+                "ts_send": t.zeros(plan.cap, dtype=t.int64, device=self.device),
+                "hash_recv": t.zeros(plan.cap * plan.world, dtype=t.int32, device=self.device),
+                "ts_recv": t.zeros(plan.cap * plan.world, dtype=t.int64, device=self.device)}
+
+    def fingerprint_into(self, pcmset, plan: SeasonPlan, seek_to_ns, ex):
+        """K1/K2 on this rank's segments, written directly into the send buffers."""
+        pcmset.fingerprint_into(ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
+                                stride=plan.stride, seek_to_ns=seek_to_ns)
+
+    def exchange(self, dist, ex, group=None):
+        dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
+        dist.all_gather_into_tensor(ex["ts_recv"], ex["ts_send"], group=group)
+
+    def season_from_gathered(self, ex, plan: SeasonPlan, world: int):
+        h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])
+        return self.engine.HashSet.view(self.ctx, h.data_ptr(), t.data_ptr(), plan.dev_offset, plan.seg_len,
+                                        keepalive=(h, t))
 
     def match(self, season, params, pairs) -> np.ndarray:
         if len(pairs) == 0:
@@ -165,14 +187,41 @@ class GpuBackend:
         rs.free()
         return runs
 
-    def alloc_exchange(self, plan: SeasonPlan):
-        t = self.torch
-        send = t.zeros(plan.block_bytes, dtype=t.uint8, device=self.device)
-        recv = t.zeros(plan.block_bytes * plan.world, dtype=t.uint8, device=self.device)
-        return send, recv
-
     def gather_runs(self, dist, runs, group=None):
-        return gather_runs(dist, runs, self.device, self.torch, group)
+        """Every rank contributes its (host, sorted) run list; rank 0 gets all of them.
+        Two collectives: the counts (8 bytes per rank), then one block per rank sized by
+        the largest count (rounded up to a power of two so the buffers are reused)."""
+        t = self.torch
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        n = runs.shape[0]
+        if self._cnt_bufs is None:
+            self._cnt_bufs = (t.zeros(1, dtype=t.int64).pin_memory(), t.zeros(1, dtype=t.int64, device=self.device),
+                              t.zeros(world, dtype=t.int64, device=self.device))
+        h_cnt, d_cnt, d_cnts = self._cnt_bufs
+        h_cnt[0] = n
+        d_cnt.copy_(h_cnt, non_blocking=True)
+        dist.all_gather_into_tensor(d_cnts, d_cnt, group=group)
+        counts = d_cnts.cpu().numpy()
+        cap = 64
+        while cap < int(counts.max()):
+            cap *= 2
+        block = cap * RUN_DTYPE.itemsize
+        if self._run_bufs is None or self._run_bufs[0].numel() != block:
+            self._run_bufs = (t.zeros(block, dtype=t.uint8).pin_memory(),
+                              t.zeros(block, dtype=t.uint8, device=self.device),
+                              t.zeros(block * world, dtype=t.uint8, device=self.device),
+                              t.zeros(block * world, dtype=t.uint8).pin_memory())
+        h_send, d_send, d_recv, h_recv = self._run_bufs
+        if n:
+            h_send.numpy()[:n * RUN_DTYPE.itemsize] = np.frombuffer(runs.tobytes(), dtype=np.uint8)
+        d_send.copy_(h_send, non_blocking=True)
+        dist.all_gather_into_tensor(d_recv, d_send, group=group)
+        if rank != 0:
+            return None
+        h_recv.copy_(d_recv, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        return unpack_run_blocks(h_recv.numpy(), counts, block)
 
     def vote(self, hash_duration_ns, params, runs, pairs):
         return self.engine.vote(hash_duration_ns, params, runs, pairs=pairs)
@@ -181,31 +230,11 @@ class GpuBackend:
         obj.free()
 
 
-def gather_runs(dist, runs: np.ndarray, device, torch, group=None) -> list | None:
-    """All ranks contribute a run list; rank 0 gets the list of arrays.  Two
-    fixed-size collectives (counts, then padded payload): no pickling."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    cnt = torch.tensor([runs.shape[0]], dtype=torch.int64, device=device)
-    counts = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, cnt, group=group)
-    counts = counts.cpu().numpy()
-    cap = int(counts.max())
-    if cap == 0:
-        return [np.zeros(0, dtype=RUN_DTYPE) for _ in range(world)] if rank == 0 else None
-    send = torch.zeros(cap * RUN_DTYPE.itemsize, dtype=torch.uint8, device=device)
-    if runs.shape[0]:
-        raw = torch.from_numpy(np.frombuffer(runs.tobytes(), dtype=np.uint8).copy())
-        send[:raw.numel()] = raw.to(device)
-    recv = torch.zeros(world * cap * RUN_DTYPE.itemsize, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    if rank != 0:
-        return None
-    host = recv.cpu().numpy()
+def unpack_run_blocks(buf: np.ndarray, counts, block: int) -> list:
     out = []
-    for r in range(world):
-        blk = host[r * cap * RUN_DTYPE.itemsize:(r * cap + int(counts[r])) * RUN_DTYPE.itemsize]
-        out.append(np.frombuffer(blk.tobytes(), dtype=RUN_DTYPE).copy())
+    for r, n in enumerate(counts):
+        body = buf[r * block:r * block + int(n) * RUN_DTYPE.itemsize]
+        out.append(np.frombuffer(body.tobytes(), dtype=RUN_DTYPE).copy())
     return out
 
 
@@ -236,7 +265,7 @@ class SeasonJob:
         self.slices = shard_pairs(self.plan.seg_len, self.pairs, self.world, bool(params.include_endings))
         self.local_segs = self.plan.local_segments(self.rank)
         self.local_seek = self.seek_to_ns[self.local_segs] if self.local_segs else np.zeros(0, np.uint64)
-        self._send = self._recv = None
+        self._ex = None
 
     # which of the global segments this rank must be given
     def local_segment_ids(self):
@@ -247,9 +276,9 @@ class SeasonJob:
         return self.backend.upload_pcm(local_segments)
 
     def _buffers(self):
-        if self._send is None:
-            self._send, self._recv = self.backend.alloc_exchange(self.plan)
-        return self._send, self._recv
+        if self._ex is None:
+            self._ex = self.backend.alloc_exchange(self.plan)
+        return self._ex
 
     def run_resident(self, pcmset):
         """fingerprint -> all-gather -> match -> gather -> vote.  Returns the list of
@@ -258,24 +287,19 @@ class SeasonJob:
         if self.world == 1 and self._all_pairs and hasattr(b, "fingerprint_search"):
             # one GPU, default pair list: no exchange buffers, two C-ABI calls
             return b.fingerprint_search(pcmset, self.plan, self.local_seek, self.hash_duration_ns, self.params)
-        send, recv = self._buffers()
-        b.fingerprint_into(pcmset, self.plan, self.local_seek, send)
+        ex = self._buffers()
+        b.fingerprint_into(pcmset, self.plan, self.local_seek, ex)
         if self.world > 1:
-            self.dist.all_gather_into_tensor(recv, send, group=self.group)
-        else:
-            recv = send
-        season = b.season_from_gathered(recv, self.plan)
+            b.exchange(self.dist, ex, self.group)
+        season = b.season_from_gathered(ex, self.plan, self.world)
         start, end = self.slices[self.rank]
         runs = b.match(season, self.params, self.pairs[start:end])
-        if self.world > 1:
-            gathered = b.gather_runs(self.dist, runs, self.group)
-        else:
-            gathered = [runs]
+        b.release(season)
+        gathered = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else [runs]
         results = None
         if self.rank == 0:
             all_runs = merge_runs(gathered, self.slices)
             results = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
-        b.release(season)
         return results
 
     def run_host(self, local_segments):

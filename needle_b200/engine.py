@@ -208,6 +208,18 @@ class HashSet:
               "nb200_hashset_from_device_scattered")
         return HashSet(ctx, out)
 
+    @staticmethod
+    def view(ctx: Context, d_hashes: int, d_ts_ns: int, dev_offset, seg_len, keepalive=None) -> "HashSet":
+        """nb200_hashset_view: a season over caller-owned device arrays (not copied)."""
+        do = np.ascontiguousarray(dev_offset, dtype=np.uint64)
+        ln = np.ascontiguousarray(seg_len, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_hashset_view(ctx.handle, C.c_void_p(d_hashes), C.c_void_p(d_ts_ns), ptr(do), ptr(ln),
+                                       ln.size // 2, C.byref(out)), "nb200_hashset_view")
+        hs = HashSet(ctx, out)
+        hs._keepalive = keepalive
+        return hs
+
     def info(self):
         n = C.c_uint32(0)
         total = C.c_uint64(0)
@@ -253,6 +265,17 @@ class HashSet:
             self.free()
         except Exception:
             pass
+
+
+def fingerprint_layout(n_mono_per_segment, stride: int = 2):
+    """nb200_fingerprint_layout -> (dev_offset[], seg_len[], total) of the device layout."""
+    n = np.ascontiguousarray(n_mono_per_segment, dtype=np.uint64)
+    off = np.zeros(n.size, np.uint64)
+    ln = np.zeros(n.size, np.uint64)
+    total = C.c_uint64(0)
+    check(lib().nb200_fingerprint_layout(ptr(n), n.size, stride, ptr(off), ptr(ln), C.byref(total)),
+          "nb200_fingerprint_layout")
+    return off, ln, total.value
 
 
 class RunSet:
@@ -312,6 +335,14 @@ class PcmSet:
         check(lib().nb200_fingerprint_run(self.ctx.handle, self._h, stride, delay_ns, item_ns, ptr(seek),
                                           C.byref(out)), "nb200_fingerprint_run")
         return HashSet(self.ctx, out)
+
+    def fingerprint_into(self, d_hashes: int, d_ts_ns: int, capacity: int, stride: int = 2,
+                         delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS, seek_to_ns=None):
+        """nb200_fingerprint_run_into: hashes + timestamps straight into caller-owned device arrays."""
+        seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        check(lib().nb200_fingerprint_run_into(self.ctx.handle, self._h, stride, delay_ns, item_ns, ptr(seek),
+                                               C.c_void_p(d_hashes), C.c_void_p(d_ts_ns), capacity),
+              "nb200_fingerprint_run_into")
 
     def free(self):
         if self._h:

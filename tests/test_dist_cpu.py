@@ -34,12 +34,19 @@ def test_plans_cover_everything_once():
         plan = nd.SeasonPlan.build(n_mono, world)
         seen = sorted(v for vs in plan.videos_of_rank for v in vs)
         assert seen == list(range(13))
-        # segments do not overlap inside the receive buffer
-        spans = sorted((int(plan.src_hash_off[s]), int(plan.src_hash_off[s] + plan.seg_len[s])) for s in range(26))
+        # segments do not overlap inside the receive buffers, start 4-aligned, stay in their rank's block
+        spans = sorted((int(plan.dev_offset[s]), int(plan.dev_offset[s] + plan.seg_len[s])) for s in range(26))
         assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+        assert all(int(o) % 4 == 0 for o in plan.dev_offset) and plan.cap % 4 == 0
         for r, vs in enumerate(plan.videos_of_rank):
-            used = sum(int(plan.seg_len[2 * v] + plan.seg_len[2 * v + 1]) for v in vs)
-            assert used <= plan.cap
+            for v in vs:
+                for e in (0, 1):
+                    s = 2 * v + e
+                    assert r * plan.cap <= plan.dev_offset[s] and plan.dev_offset[s] + plan.seg_len[s] <= (r + 1) * plan.cap
+        # the python layout equals the library's (nb200_fingerprint_layout)
+        off, ln, total = engine.fingerprint_layout(n_mono, 2)
+        o2, l2, t2 = nd.device_layout(n_mono, 2)
+        assert off.tolist() == o2 and ln.tolist() == l2 and total == t2
         pairs = nd.pair_list(13)
         sl = nd.shard_pairs(plan.seg_len, pairs, world, True)
         assert sl[0][0] == 0 and sl[-1][1] == len(pairs)
@@ -61,27 +68,31 @@ class OracleBackend:
 
     def alloc_exchange(self, plan):
         t = self.torch
-        return t.zeros(plan.block_bytes, dtype=t.uint8), t.zeros(plan.block_bytes * plan.world, dtype=t.uint8)
+        return {"hash_send": t.zeros(plan.cap, dtype=t.int32), "ts_send": t.zeros(plan.cap, dtype=t.int64),
+                "hash_recv": t.zeros(plan.cap * plan.world, dtype=t.int32),
+                "ts_recv": t.zeros(plan.cap * plan.world, dtype=t.int64)}
 
-    def fingerprint_into(self, segs, plan, seek, send):
-        buf = send.numpy()
-        hv = buf[:4 * plan.cap].view(np.uint32)
-        tv = buf[4 * plan.cap:].view(np.uint64)
-        pos = 0
-        for pcm, sk in zip(segs, seek):
+    def fingerprint_into(self, segs, plan, seek, ex):
+        hv = ex["hash_send"].numpy().view(np.uint32)
+        tv = ex["ts_send"].numpy().view(np.uint64)
+        off, ln, _total = nd.device_layout([s.size for s in segs], plan.stride)
+        for pcm, sk, o, n in zip(segs, seek, off, ln):
             h, t = self.orc.subsample_and_stamp(self.orc.fingerprint(pcm), plan.stride, seek_to_ns=int(sk))
-            hv[pos:pos + h.size] = h
-            tv[pos:pos + h.size] = t
-            pos += h.size
+            assert h.size == n
+            hv[o:o + n] = h
+            tv[o:o + n] = t
 
-    def season_from_gathered(self, recv, plan):
-        buf = recv.numpy()
-        hv, tv = buf.view(np.uint32), buf.view(np.uint64)
+    def exchange(self, dist, ex, group=None):
+        dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
+        dist.all_gather_into_tensor(ex["ts_recv"], ex["ts_send"], group=group)
+
+    def season_from_gathered(self, ex, plan, world):
+        h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])
+        hv, tv = h.numpy().view(np.uint32), t.numpy().view(np.uint64)
         segs = []
         for s in range(2 * plan.n_videos):
-            n = int(plan.seg_len[s])
-            a, b = int(plan.src_hash_off[s]), int(plan.src_ts_off[s])
-            segs.append((hv[a:a + n].copy(), tv[b:b + n].copy()))
+            n, a = int(plan.seg_len[s]), int(plan.dev_offset[s])
+            segs.append((hv[a:a + n].copy(), tv[a:a + n].copy()))
         return H.season_from_lists(segs[0::2], segs[1::2])
 
     def match(self, season, params, pairs):
@@ -100,7 +111,24 @@ class OracleBackend:
         return H.rows_to_runs(rows)
 
     def gather_runs(self, dist, runs, group=None):
-        return nd.gather_runs(dist, runs, "cpu", self.torch, group)
+        """Same protocol as GpuBackend.gather_runs, on CPU tensors."""
+        t = self.torch
+        world = dist.get_world_size(group)
+        cnts = t.zeros(world, dtype=t.int64)
+        dist.all_gather_into_tensor(cnts, t.tensor([runs.shape[0]], dtype=t.int64), group=group)
+        counts = cnts.numpy()
+        cap = 64
+        while cap < int(counts.max()):
+            cap *= 2
+        block = cap * RUN_DTYPE.itemsize
+        send = t.zeros(block, dtype=t.uint8)
+        if runs.shape[0]:
+            send.numpy()[:runs.shape[0] * RUN_DTYPE.itemsize] = np.frombuffer(runs.tobytes(), dtype=np.uint8)
+        recv = t.zeros(block * world, dtype=t.uint8)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        if dist.get_rank(group) != 0:
+            return None
+        return nd.unpack_run_blocks(recv.numpy(), counts, block)
 
     def vote(self, hd, params, runs, pairs):
         return engine.vote(hd, params, runs, pairs=pairs)

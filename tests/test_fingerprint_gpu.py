@@ -171,3 +171,58 @@ def test_analyze_search_intervals_vs_oracle(ctx, oracle):
             assert abs(int(a) - int(b)) <= tol
         # and the detected opening really is where the intro was spliced
         assert abs(g[3] / 1e9 - ep.intro_at) < 4.0
+
+
+def test_fingerprint_into_and_hashset_view(ctx):
+    """The zero-copy multi-GPU plumbing: K2 writing into caller-owned device arrays
+    (nb200_fingerprint_run_into) and matching out of caller-owned arrays in any segment
+    placement (nb200_hashset_view) give what the ordinary owned path gives."""
+    import torch
+    eps = synth.make_pcm_season(4, 4.0, season_seed=9, intro_s=40.0, credits_s=30.0)
+    segs, seek = [], []
+    for ep in eps:
+        a, b, sk = synth.split_segments(ep.pcm)
+        segs += [a, b]
+        seek += [0, sk]
+    ps = engine.PcmSet.upload(ctx, segs)
+    hs = ps.fingerprint(stride=2, seek_to_ns=seek)
+    h, t, off = hs.download()
+    doff, dlen, total = engine.fingerprint_layout([s.size for s in segs], 2)
+    assert [int(x) for x in dlen] == [int(off[k + 1] - off[k]) for k in range(len(segs))]
+    hb = torch.zeros(total + 8, dtype=torch.int32, device="cuda")
+    tb = torch.zeros(total + 8, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ps.fingerprint_into(hb.data_ptr(), tb.data_ptr(), total + 8, stride=2, seek_to_ns=seek)
+    ctx.synchronize()
+    hv, tv = hb.cpu().numpy().view(np.uint32), tb.cpu().numpy().view(np.uint64)
+    for k in range(len(segs)):
+        a, n = int(doff[k]), int(dlen[k])
+        assert np.array_equal(hv[a:a + n], h[int(off[k]):int(off[k + 1])])
+        assert np.array_equal(tv[a:a + n], t[int(off[k]):int(off[k + 1])])
+    with pytest.raises(Nb200Error):
+        ps.fingerprint_into(hb.data_ptr(), tb.data_ptr(), total - 4, stride=2, seek_to_ns=seek)   # too small
+    p = engine.match_params(include_endings=True)
+    want = hs.match(p).download()
+    assert want.shape[0] >= 6
+    view = engine.HashSet.view(ctx, hb.data_ptr(), tb.data_ptr(), doff, dlen, keepalive=(hb, tb))
+    assert np.array_equal(view.match(p).download(), want)
+    hd = np.full(4, synth.HASH_DURATION_NS, np.uint64)
+    assert view.search(hd, p) == hs.search(hd, p)
+    # videos in reverse order through the offsets alone == uploading the reversed season
+    order = [3, 2, 1, 0]
+    roff = np.array([doff[2 * v + e] for v in order for e in (0, 1)], np.uint64)
+    rlen = np.array([dlen[2 * v + e] for v in order for e in (0, 1)], np.uint64)
+    rview = engine.HashSet.view(ctx, hb.data_ptr(), tb.data_ptr(), roff, rlen, keepalive=(hb, tb))
+    hs_l, ts_l, off_l = [], [], [0]
+    for v in order:
+        for e in (0, 1):
+            k = 2 * v + e
+            hs_l.append(h[int(off[k]):int(off[k + 1])])
+            ts_l.append(t[int(off[k]):int(off[k + 1])])
+            off_l.append(off_l[-1] + hs_l[-1].size)
+    rev = engine.HashSet.upload(ctx, np.concatenate(hs_l), np.concatenate(ts_l), np.asarray(off_l, np.uint64))
+    assert np.array_equal(rview.match(p).download(), rev.match(p).download())
+    assert rview.search(hd, p) == rev.search(hd, p)
+    with pytest.raises(Nb200Error) as e:
+        engine.HashSet.view(ctx, hb.data_ptr(), tb.data_ptr(), doff + np.uint64(1), dlen)     # not 4-aligned
+    assert e.value.status == ERR_INVALID_ARGUMENT
