@@ -224,6 +224,8 @@ def run_reference(args):
 # ------------------------------------------------------------------ b200 arm
 
 def run_b200(args):
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"    # NCCL's version banner goes to stdout; this run prints one JSON line
     import torch
     from needle_b200 import dist as nd
     from needle_b200 import engine
@@ -310,6 +312,7 @@ def run_b200(args):
     barrier()
     launches0 = ctx.last_kernel_ms()["n_launches"]
     ctx.host_profile(reset=True)
+    job.phase_s = {}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
     ev0.record()
@@ -324,6 +327,7 @@ def run_b200(args):
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.last_kernel_ms()["n_launches"] - launches0
     host_ms = {k: v / args.steps for k, v in ctx.host_profile(reset=True).items()}
+    job_ms = {k: v * 1e3 / args.steps for k, v in job.phase_s.items()}
     for k in kernel_ms:
         kernel_ms[k] /= args.steps
 
@@ -414,6 +418,7 @@ def run_b200(args):
         "audio_hours_per_sec": hours_total / (step_ms * 1e-3),
         "kernel_ms_per_step": kernel_ms,
         "host_phase_ms_per_step": host_ms,
+        "job_phase_ms_per_step_rank0": job_ms,
         # the schema's roofline object, for the kernel with the largest share of the step
         "roofline": {
             "kernel": dominant, "bound": "hbm",

@@ -271,6 +271,14 @@ int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t 
                                uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
                                void *d_hashes_out, void *d_ts_ns_out, uint64_t capacity);
 
+/* nb200_pcmset_upload + nb200_fingerprint_run_into in one call for MONO host PCM
+ * (pinned for full rate): the H2D copy runs in chunks on a second stream while K1
+ * already works on the chunks that have landed.  n_segments must be even. */
+int nb200_fingerprint_host_into(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples,
+                                uint32_t n_segments, uint32_t stride, uint64_t delay_ns, uint64_t item_ns,
+                                const uint64_t *seek_to_ns, void *d_hashes_out, void *d_ts_ns_out,
+                                uint64_t capacity);
+
 /* One-shot with host buffers: raw sub-fingerprints (stride 1, no timestamps)
  * of each segment == chromaprint_get_raw_fingerprint.  out_hashes[k] is
  * nb200_free'd by the caller. */

@@ -1143,6 +1143,23 @@ int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t 
     return NB200_OK;
 }
 
+int nb200_fingerprint_host_into(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples,
+                                uint32_t n_segments, uint32_t stride, uint64_t delay_ns, uint64_t item_ns,
+                                const uint64_t *seek_to_ns, void *d_hashes_out, void *d_ts_ns_out,
+                                uint64_t capacity) {
+    if (!ctx || !pcm || !n_samples || !d_hashes_out || !d_ts_ns_out) return NB200_ERR_NULL_ARGUMENT;
+    nb200_pcmset *ps = nullptr;
+    NB_TRY(pcmset_make(ctx, pcm, n_samples, 1, n_segments, false, &ps));
+    int st = ensure_fp_tables(ctx);
+    nb200_hashset *hs = nullptr;
+    if (st == NB200_OK)
+        st = fingerprint_run_pipelined(ctx, ps, pcm, stride, delay_ns, item_ns, seek_to_ns, &hs, d_hashes_out,
+                                       d_ts_ns_out, capacity);
+    nb200_hashset_free(hs);
+    nb200_pcmset_free(ps);   // kernels have completed (fingerprint_run_pipelined synchronises)
+    return st;
+}
+
 int nb200_fingerprint_batch(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
                             int channels, uint32_t n_segments, uint32_t stride, uint32_t **out_hashes,
                             uint64_t *out_counts) {

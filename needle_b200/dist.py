@@ -170,6 +170,11 @@ class GpuBackend:
         pcmset.fingerprint_into(ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
                                 stride=plan.stride, seek_to_ns=seek_to_ns)
 
+    def fingerprint_host_into(self, segments, plan: SeasonPlan, seek_to_ns, ex):
+        """Host PCM -> (H2D in chunks underneath K1) -> K2 into the send buffers."""
+        self.ctx.fingerprint_host_into(segments, ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
+                                       stride=plan.stride, seek_to_ns=seek_to_ns)
+
     def exchange(self, dist, ex, group=None):
         dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
         dist.all_gather_into_tensor(ex["ts_recv"], ex["ts_send"], group=group)
@@ -266,6 +271,13 @@ class SeasonJob:
         self.local_segs = self.plan.local_segments(self.rank)
         self.local_seek = self.seek_to_ns[self.local_segs] if self.local_segs else np.zeros(0, np.uint64)
         self._ex = None
+        self.phase_s = {}      # wall seconds per phase of run_resident / run_host on this rank (accumulated)
+
+    def _tick(self, name, t0):
+        import time
+        t1 = time.perf_counter()
+        self.phase_s[name] = self.phase_s.get(name, 0.0) + (t1 - t0)
+        return t1
 
     # which of the global segments this rank must be given
     def local_segment_ids(self):
@@ -287,24 +299,46 @@ class SeasonJob:
         if self.world == 1 and self._all_pairs and hasattr(b, "fingerprint_search"):
             # one GPU, default pair list: no exchange buffers, two C-ABI calls
             return b.fingerprint_search(pcmset, self.plan, self.local_seek, self.hash_duration_ns, self.params)
+        import time
+        t = time.perf_counter()
         ex = self._buffers()
         b.fingerprint_into(pcmset, self.plan, self.local_seek, ex)
+        t = self._tick("fingerprint", t)
+        return self._after_fingerprint(ex, t)
+
+    def _after_fingerprint(self, ex, t):
+        b = self.backend
         if self.world > 1:
             b.exchange(self.dist, ex, self.group)
         season = b.season_from_gathered(ex, self.plan, self.world)
+        t = self._tick("exchange_enqueue", t)
         start, end = self.slices[self.rank]
         runs = b.match(season, self.params, self.pairs[start:end])
         b.release(season)
+        t = self._tick("match", t)
         gathered = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else [runs]
+        t = self._tick("gather_runs", t)
         results = None
         if self.rank == 0:
             all_runs = merge_runs(gathered, self.slices)
             results = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
+            self._tick("vote", t)
         return results
 
     def run_host(self, local_segments):
-        ps = self.upload(local_segments)
-        try:
-            return self.run_resident(ps)
-        finally:
-            self.backend.release(ps)
+        """From host PCM (pinned for full PCIe rate).  The copy is pipelined under K1
+        when the backend can stream (GpuBackend.fingerprint_host_into)."""
+        b = self.backend
+        one_gpu = self.world == 1 and self._all_pairs and hasattr(b, "fingerprint_search")
+        if one_gpu or not hasattr(b, "fingerprint_host_into"):
+            ps = self.upload(local_segments)
+            try:
+                return self.run_resident(ps)
+            finally:
+                b.release(ps)
+        import time
+        t = time.perf_counter()
+        ex = self._buffers()
+        b.fingerprint_host_into(local_segments, self.plan, self.local_seek, ex)
+        t = self._tick("upload+fingerprint", t)
+        return self._after_fingerprint(ex, t)

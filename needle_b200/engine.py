@@ -143,6 +143,19 @@ class Context:
             lib().nb200_free(outs[k])
         return res
 
+    def fingerprint_host_into(self, segments, d_hashes: int, d_ts_ns: int, capacity: int, stride: int = 2,
+                              delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS, seek_to_ns=None):
+        """nb200_fingerprint_host_into: mono host PCM streamed in under K1, hashes and
+        timestamps written into caller-owned device arrays."""
+        segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]
+        n = len(segs)
+        ptrs = (C.c_void_p * max(n, 1))(*[s.ctypes.data for s in segs])
+        cnt = np.asarray([s.size for s in segs], dtype=np.uint64)
+        seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        check(lib().nb200_fingerprint_host_into(self._h, ptrs, ptr(cnt), n, stride, delay_ns, item_ns, ptr(seek),
+                                                C.c_void_p(d_hashes), C.c_void_p(d_ts_ns), capacity),
+              "nb200_fingerprint_host_into")
+
     def analyze_search(self, segments, channels, seek_to_ns, hash_duration_ns, params: MatchParams):
         """nb200_analyze_search: segments = [opening_0, ending_0, opening_1, ...] PCM arrays."""
         segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]
