@@ -184,6 +184,13 @@ int nb200_vote(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32
                uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
                uint64_t n_runs, nb200_search_result *results);
 
+/* nb200_vote for the videos v with video_mask[v] != 0 only (NULL = all); the others get
+ * present = 0.  All runs are still needed (a video's candidates come from every pair it
+ * is in).  Lets the ranks of a multi-GPU job split the per-video work. */
+int nb200_vote_subset(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                      uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
+                      uint64_t n_runs, const uint8_t *video_mask, nb200_search_result *results);
+
 /* ------------------------------------------ device-resident staged pipeline */
 
 int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,

@@ -68,6 +68,10 @@ class SearchResultC(C.Structure):
                 self.opening_end_ns, self.ending_start_ns, self.ending_end_ns)
 
 
+RESULT_DTYPE = np.dtype([("present", "<u4"), ("has_opening", "<u4"), ("has_ending", "<u4"), ("reserved", "<u4"),
+                         ("opening_start_ns", "<u8"), ("opening_end_ns", "<u8"),
+                         ("ending_start_ns", "<u8"), ("ending_end_ns", "<u8")])
+
 # name -> (restype, argtypes); every symbol include/needle_b200.h declares
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -93,6 +97,8 @@ PROTOTYPES = {
     "nb200_search_hashset": (C.c_int, [_P, _P, _P, C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
     "nb200_vote": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, C.POINTER(MatchParams),
                              _P, C.c_uint64, C.POINTER(SearchResultC)]),
+    "nb200_vote_subset": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, C.POINTER(MatchParams),
+                                    _P, C.c_uint64, _P, C.POINTER(SearchResultC)]),
     "nb200_hashset_upload": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _PP]),
     "nb200_hashset_info": (C.c_int, [_P, C.POINTER(C.c_uint32), _U64P, _P]),
     "nb200_hashset_download": (C.c_int, [_P, _P, _P, _P]),

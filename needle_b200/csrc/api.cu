@@ -578,7 +578,15 @@ int nb200_vote(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32
                uint64_t n_runs, nb200_search_result *results) {
     if (!hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
     if (n_runs > 0 && !runs) return NB200_ERR_NULL_ARGUMENT;
-    return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs, n_runs, results);
+    return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs, n_runs, nullptr, results);
+}
+
+int nb200_vote_subset(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                      uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
+                      uint64_t n_runs, const uint8_t *video_mask, nb200_search_result *results) {
+    if (!hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_runs > 0 && !runs) return NB200_ERR_NULL_ARGUMENT;
+    return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs, n_runs, video_mask, results);
 }
 
 int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
@@ -589,7 +597,7 @@ int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
     nb200_run *runs = nullptr;
     uint64_t n_runs = 0;
     NB_TRY(nb200_match_pairs(ctx, hashes, ts_ns, seg_offset, n_videos, nullptr, 0, params, &runs, &n_runs));
-    int st = vote_impl(hash_duration_ns, n_videos, nullptr, 0, params, runs, n_runs, results);
+    int st = vote_impl(hash_duration_ns, n_videos, nullptr, 0, params, runs, n_runs, nullptr, results);
     free(runs);
     return st;
 }
@@ -607,7 +615,7 @@ int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t
     int st = nb200_runset_download(ctx, rs, runs.data());
     if (st == NB200_OK) {
         PhaseTimer pt(ctx, NB200_PHASE_VOTE);
-        st = vote_impl(hash_duration_ns, hs->n_videos, nullptr, 0, params, runs.data(), rs->n_runs, results);
+        st = vote_impl(hash_duration_ns, hs->n_videos, nullptr, 0, params, runs.data(), rs->n_runs, nullptr, results);
     }
     nb200_runset_free(rs);
     return st;

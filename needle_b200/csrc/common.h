@@ -230,7 +230,7 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pai
 void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order
 int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
-              uint64_t n_runs, nb200_search_result *results);
+              uint64_t n_runs, const uint8_t *video_mask, nb200_search_result *results);
 
 // fingerprint.cu -----------------------------------------------------------
 int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,

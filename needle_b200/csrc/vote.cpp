@@ -87,7 +87,7 @@ struct Candidate {
 
 int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
-              uint64_t n_runs, nb200_search_result *results) {
+              uint64_t n_runs, const uint8_t *video_mask, nb200_search_result *results) {
     std::vector<uint32_t> default_flat;
     if (!pairs) {
         default_pairs(n_videos, default_flat);
@@ -150,8 +150,9 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
     const uint32_t T = params->hash_match_threshold;
     const uint32_t bias = T + T / 2;
     std::vector<Candidate> cand;
-    std::vector<uint32_t> cluster;
+    std::vector<uint32_t> cluster, uniq, mult, ucount;
     for (uint32_t v = 0; v < n_videos; v++) {
+        if (video_mask && !video_mask[v]) continue;        // another rank votes for this video
         if (vid_begin[v + 1] == vid_begin[v]) continue;   // find_best_match -> None
         cand.clear();
         for (uint64_t m = vid_begin[v]; m < vid_begin[v + 1]; m++) {
@@ -173,17 +174,37 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
         const size_t nc = cand.size();
         // |distinct_matches[i]| = #{ j : popcount(h_i ^ h_j) < T + T/2 }; i is a key iff that is > 0
         // (the relation is symmetric: visit each unordered pair once)
-        cluster.assign(nc, bias > 0 ? 1u : 0u);   // i with itself: distance 0
-        for (size_t i = 0; i < nc; i++) {
-            const uint32_t hi = cand[i].match_hash;
-            uint32_t mine = 0;
-            for (size_t j = i + 1; j < nc; j++) {
-                const uint32_t hit = (uint32_t)__builtin_popcount(hi ^ cand[j].match_hash) < bias ? 1u : 0u;
-                mine += hit;
-                cluster[j] += hit;
+        // The same intro seen from many pairs gives few distinct signatures: count over the
+        // distinct values with their multiplicities (u^2 instead of c^2 distances).
+        uniq.clear();
+        for (size_t i = 0; i < nc; i++) uniq.push_back(cand[i].match_hash);
+        std::sort(uniq.begin(), uniq.end());
+        mult.clear();
+        {
+            size_t w = 0;
+            for (size_t i = 0; i < uniq.size(); i++) {
+                if (w > 0 && uniq[w - 1] == uniq[i]) {
+                    mult[w - 1]++;
+                } else {
+                    uniq[w++] = uniq[i];
+                    mult.push_back(1);
+                }
             }
-            cluster[i] += mine;
+            uniq.resize(w);
         }
+        const size_t nu = uniq.size();
+        ucount.assign(nu, 0);
+        for (size_t a = 0; a < nu; a++) {
+            if (bias > 0) ucount[a] += mult[a];          // distance 0 to every copy of itself (including itself)
+            for (size_t b = a + 1; b < nu; b++)
+                if ((uint32_t)__builtin_popcount(uniq[a] ^ uniq[b]) < bias) {
+                    ucount[a] += mult[b];
+                    ucount[b] += mult[a];
+                }
+        }
+        cluster.resize(nc);
+        for (size_t i = 0; i < nc; i++)
+            cluster[i] = ucount[std::lower_bound(uniq.begin(), uniq.end(), cand[i].match_hash) - uniq.begin()];
 
         nb200_search_result &res = results[v];
         res.present = 1;

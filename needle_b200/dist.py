@@ -19,7 +19,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import RUN_DTYPE
+from ._lib import RESULT_DTYPE, RUN_DTYPE
 
 FRAME, HOP, WARMUP = 4096, 1365, 19
 
@@ -146,6 +146,7 @@ class GpuBackend:
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._run_bufs = None
         self._cnt_bufs = None
+        self._res_bufs = None
 
     def upload_pcm(self, segments):
         return self.engine.PcmSet.upload(self.ctx, segments)
@@ -222,17 +223,41 @@ class GpuBackend:
             h_send.numpy()[:n * RUN_DTYPE.itemsize] = np.frombuffer(runs.tobytes(), dtype=np.uint8)
         d_send.copy_(h_send, non_blocking=True)
         dist.all_gather_into_tensor(d_recv, d_send, group=group)
-        if rank != 0:
-            return None
-        h_recv.copy_(d_recv, non_blocking=True)
+        h_recv.copy_(d_recv, non_blocking=True)          # every rank: each votes for its share of the videos
         t.cuda.current_stream(self.device).synchronize()
         return unpack_run_blocks(h_recv.numpy(), counts, block)
 
-    def vote(self, hash_duration_ns, params, runs, pairs):
-        return self.engine.vote(hash_duration_ns, params, runs, pairs=pairs)
+    def gather_results(self, dist, mine: np.ndarray, cap: int, group=None):
+        """Each rank's rows of the result table (cap rows, padded) -> all rows on rank 0."""
+        t = self.torch
+        world = dist.get_world_size(group)
+        nbytes = cap * RESULT_DTYPE.itemsize
+        if self._res_bufs is None or self._res_bufs[0].numel() != nbytes:
+            self._res_bufs = (t.zeros(nbytes, dtype=t.uint8).pin_memory(),
+                              t.zeros(nbytes, dtype=t.uint8, device=self.device),
+                              t.zeros(nbytes * world, dtype=t.uint8, device=self.device),
+                              t.zeros(nbytes * world, dtype=t.uint8).pin_memory())
+        h_send, d_send, d_recv, h_recv = self._res_bufs
+        h_send.numpy()[:mine.shape[0] * RESULT_DTYPE.itemsize] = np.frombuffer(mine.tobytes(), dtype=np.uint8)
+        d_send.copy_(h_send, non_blocking=True)
+        dist.all_gather_into_tensor(d_recv, d_send, group=group)
+        if dist.get_rank(group) != 0:
+            return None
+        h_recv.copy_(d_recv, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        return np.frombuffer(h_recv.numpy().tobytes(), dtype=RESULT_DTYPE).reshape(world, cap)
+
+    def vote(self, hash_duration_ns, params, runs, pairs, video_mask=None) -> np.ndarray:
+        return self.engine.vote_array(hash_duration_ns, params, runs, pairs=pairs, video_mask=video_mask)
 
     def release(self, obj):
         obj.free()
+
+
+def results_rows_as_tuples(arr: np.ndarray):
+    f = ("present", "has_opening", "has_ending", "opening_start_ns", "opening_end_ns", "ending_start_ns",
+         "ending_end_ns")
+    return list(zip(*[arr[k].tolist() for k in f])) if arr.shape[0] else []
 
 
 def unpack_run_blocks(buf: np.ndarray, counts, block: int) -> list:
@@ -318,12 +343,28 @@ class SeasonJob:
         t = self._tick("match", t)
         gathered = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else [runs]
         t = self._tick("gather_runs", t)
-        results = None
-        if self.rank == 0:
-            all_runs = merge_runs(gathered, self.slices)
-            results = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
+        # the vote is per video and needs every run: all ranks have them, each votes for
+        # the videos v with v % world == rank, rank 0 collects the rows
+        all_runs = merge_runs(gathered, self.slices)
+        n_videos = self.plan.n_videos
+        if self.world == 1:
+            table = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
             self._tick("vote", t)
-        return results
+            return results_rows_as_tuples(table)
+        mask = np.zeros(n_videos, np.uint8)
+        mask[self.rank::self.world] = 1
+        table = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs, video_mask=mask)
+        t = self._tick("vote", t)
+        cap = (n_videos + self.world - 1) // self.world
+        rows = b.gather_results(self.dist, table[self.rank::self.world], cap, self.group)
+        if self.rank != 0:
+            return None
+        full = np.zeros(n_videos, dtype=RESULT_DTYPE)
+        for r in range(self.world):
+            k = len(range(r, n_videos, self.world))
+            full[r::self.world] = rows[r, :k]
+        self._tick("gather_results", t)
+        return results_rows_as_tuples(full)
 
     def run_host(self, local_segments):
         """From host PCM (pinned for full PCIe rate).  The copy is pipelined under K1

@@ -170,6 +170,26 @@ class Context:
         return _results_list(res, n // 2)
 
 
+def vote_array(hash_duration_ns, params: MatchParams, runs: np.ndarray, pairs=None, video_mask=None) -> np.ndarray:
+    """nb200_vote / nb200_vote_subset (host only) -> structured array, one row per video."""
+    hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
+    r = np.ascontiguousarray(runs, dtype=RUN_DTYPE)
+    n_videos = hd.size
+    _keep, pp, npairs = _pairs_arg(pairs)
+    out = np.zeros(max(n_videos, 1), dtype=_lib.RESULT_DTYPE)
+    res = C.cast(out.ctypes.data_as(C.c_void_p), C.POINTER(SearchResultC))
+    mask = None if video_mask is None else np.ascontiguousarray(video_mask, dtype=np.uint8)
+    check(lib().nb200_vote_subset(ptr(hd), n_videos, pp, npairs, C.byref(params), ptr(r), r.shape[0], ptr(mask),
+                                  res), "nb200_vote_subset")
+    return out[:n_videos]
+
+
+def results_as_tuples(arr: np.ndarray):
+    f = ("present", "has_opening", "has_ending", "opening_start_ns", "opening_end_ns", "ending_start_ns",
+         "ending_end_ns")
+    return list(zip(*[arr[k].tolist() for k in f])) if arr.shape[0] else []
+
+
 def vote(hash_duration_ns, params: MatchParams, runs: np.ndarray, pairs=None):
     """nb200_vote (host only): runs as returned by match_pairs / RunSet.download;
     one hash duration per video."""

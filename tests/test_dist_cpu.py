@@ -126,12 +126,23 @@ class OracleBackend:
             send.numpy()[:runs.shape[0] * RUN_DTYPE.itemsize] = np.frombuffer(runs.tobytes(), dtype=np.uint8)
         recv = t.zeros(block * world, dtype=t.uint8)
         dist.all_gather_into_tensor(recv, send, group=group)
-        if dist.get_rank(group) != 0:
-            return None
         return nd.unpack_run_blocks(recv.numpy(), counts, block)
 
-    def vote(self, hd, params, runs, pairs):
-        return engine.vote(hd, params, runs, pairs=pairs)
+    def gather_results(self, dist, mine, cap, group=None):
+        t = self.torch
+        from needle_b200._lib import RESULT_DTYPE
+        world = dist.get_world_size(group)
+        nbytes = cap * RESULT_DTYPE.itemsize
+        send = t.zeros(nbytes, dtype=t.uint8)
+        send.numpy()[:mine.shape[0] * RESULT_DTYPE.itemsize] = np.frombuffer(mine.tobytes(), dtype=np.uint8)
+        recv = t.zeros(nbytes * world, dtype=t.uint8)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        if dist.get_rank(group) != 0:
+            return None
+        return np.frombuffer(recv.numpy().tobytes(), dtype=RESULT_DTYPE).reshape(world, cap)
+
+    def vote(self, hd, params, runs, pairs, video_mask=None):
+        return engine.vote_array(hd, params, runs, pairs=pairs, video_mask=video_mask)
 
     def release(self, obj):
         pass

@@ -74,3 +74,23 @@ def test_heap_order_matters(oracle):
     runs = rows_to_runs(H.entries_as_runs(entries))
     got = engine.vote(season.hash_duration_ns, engine.match_params(**kw), runs)
     assert got == want
+
+
+def test_vote_subset_partitions_the_videos(oracle):
+    """nb200_vote_subset over disjoint video masks reassembles nb200_vote (the
+    multi-GPU job splits the vote this way)."""
+    season = synth.make_hash_season(7, 420, 260, seed=6, run_len=150, jitter_len=True)
+    kw = H.params_kw(include_endings=True)
+    _, want, entries = H.oracle_run(oracle, season, **kw)
+    runs = rows_to_runs(H.entries_as_runs(entries))
+    p = engine.match_params(**kw)
+    full = engine.vote_array(season.hash_duration_ns, p, runs)
+    assert engine.results_as_tuples(full) == want
+    merged = np.zeros_like(full)
+    for r in range(3):
+        mask = np.zeros(7, np.uint8)
+        mask[r::3] = 1
+        part = engine.vote_array(season.hash_duration_ns, p, runs, video_mask=mask)
+        assert not part["present"][mask == 0].any()
+        merged[r::3] = part[r::3]
+    assert np.array_equal(merged, full)
