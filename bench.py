@@ -395,6 +395,14 @@ def run_b200(args):
     hours_total = world * sum(x.size for x in local_segments) / synth.SAMPLE_RATE / 3600.0
     step_ms = dev_ms / args.steps
     dominant = "fp_fft_chroma" if kernel_ms["fp_fft_chroma"] >= kernel_ms["match"] else "match"
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture
+    # (dram__bytes_read.sum + dram__bytes_write.sum); only valid for the shapes it was taken on
+    traffic, traffic_src = None, None
+    if args.episodes == EPISODES and args.minutes == MINUTES:
+        if dominant == "fp_fft_chroma":
+            traffic, traffic_src = 556.70e6 + 14.29e6, "profiles/r01_ncu_k1_fp_fft_chroma_v2.txt"
+        else:
+            traffic, traffic_src = 0.56e6, "profiles/r01_ncu_k3_match_fast_v2.txt"
     line = {
         "metric": "episode_pairs_per_sec", "value": n_pairs_total / (step_ms * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
@@ -424,7 +432,8 @@ def run_b200(args):
             "kernel": dominant, "bound": "hbm",
             "achieved": (frames_local * BYTES_PER_FRAME / k1_s / 1e9) if dominant == "fp_fft_chroma" else
                         (4 * sl.sum() / k3_s / 1e9),
-            "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": hbm_src,
+            "peak": hbm_peak, "unit": "GB/s", "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": hbm_src,
             "note": "neither kernel is HBM-bound (SURVEY.md 8d: 49 flop/B and 1 POPC per 4e-4 B); "
                     "the binding rooflines are roofline_fp32 (K1) and roofline_popc (K3) below",
         },

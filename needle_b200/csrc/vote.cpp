@@ -196,11 +196,14 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
         ucount.assign(nu, 0);
         for (size_t a = 0; a < nu; a++) {
             if (bias > 0) ucount[a] += mult[a];          // distance 0 to every copy of itself (including itself)
-            for (size_t b = a + 1; b < nu; b++)
-                if ((uint32_t)__builtin_popcount(uniq[a] ^ uniq[b]) < bias) {
-                    ucount[a] += mult[b];
-                    ucount[b] += mult[a];
-                }
+            const uint32_t ha = uniq[a], ma = mult[a];
+            uint32_t mine = 0;
+            for (size_t b = a + 1; b < nu; b++) {      // branch-free: the outcome is data-random
+                const uint32_t hit = (uint32_t)__builtin_popcount(ha ^ uniq[b]) < bias ? 1u : 0u;
+                mine += hit * mult[b];
+                ucount[b] += hit * ma;
+            }
+            ucount[a] += mine;
         }
         cluster.resize(nc);
         for (size_t i = 0; i < nc; i++)

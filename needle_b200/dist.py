@@ -131,6 +131,15 @@ def merge_runs(per_rank_runs, slices) -> np.ndarray:
     return np.concatenate(out) if out else np.zeros(0, dtype=RUN_DTYPE)
 
 
+def globalize_runs(runs: np.ndarray, slice_start: int) -> np.ndarray:
+    """Pair indices relative to this rank's slice -> indices into the global pair list
+    (done on the sending side, so the receiver only concatenates)."""
+    if slice_start:
+        runs = runs.copy()
+        runs["pair"] += np.uint32(slice_start)
+    return runs
+
+
 class GpuBackend:
     """The product compute path: libneedle_b200.so on this rank's GPU, running
     on torch's current stream so that NCCL collectives order with the kernels."""
@@ -260,12 +269,12 @@ def results_rows_as_tuples(arr: np.ndarray):
     return list(zip(*[arr[k].tolist() for k in f])) if arr.shape[0] else []
 
 
-def unpack_run_blocks(buf: np.ndarray, counts, block: int) -> list:
-    out = []
-    for r, n in enumerate(counts):
-        body = buf[r * block:r * block + int(n) * RUN_DTYPE.itemsize]
-        out.append(np.frombuffer(body.tobytes(), dtype=RUN_DTYPE).copy())
-    return out
+def unpack_run_blocks(buf: np.ndarray, counts, block: int) -> np.ndarray:
+    """Padded per-rank blocks -> one run array (rank order = pair order)."""
+    parts = [buf[r * block:r * block + int(n) * RUN_DTYPE.itemsize] for r, n in enumerate(counts) if n]
+    if not parts:
+        return np.zeros(0, dtype=RUN_DTYPE)
+    return np.frombuffer(np.concatenate(parts).tobytes(), dtype=RUN_DTYPE)
 
 
 class SeasonJob:
@@ -338,14 +347,13 @@ class SeasonJob:
         season = b.season_from_gathered(ex, self.plan, self.world)
         t = self._tick("exchange_enqueue", t)
         start, end = self.slices[self.rank]
-        runs = b.match(season, self.params, self.pairs[start:end])
+        runs = globalize_runs(b.match(season, self.params, self.pairs[start:end]), start)
         b.release(season)
         t = self._tick("match", t)
-        gathered = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else [runs]
+        all_runs = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else runs
         t = self._tick("gather_runs", t)
         # the vote is per video and needs every run: all ranks have them, each votes for
         # the videos v with v % world == rank, rank 0 collects the rows
-        all_runs = merge_runs(gathered, self.slices)
         n_videos = self.plan.n_videos
         if self.world == 1:
             table = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
