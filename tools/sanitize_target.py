@@ -1,0 +1,32 @@
+"""Small run of every kernel for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys
+import numpy as np
+sys.path.insert(0, ".")
+from needle_b200 import engine, synth
+
+ctx = engine.Context(0)
+rng = np.random.default_rng(0)
+# fingerprint: ragged segments, every K1 variant, stereo, pipelined host path
+lens = [0, 4095, 4096, 4096 + 1365 * 19, 4096 + 1365 * 40 + 7, 60_001, 90_000, 33_333]
+segs = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
+ref = None
+for variant in (0, 4, 5, 6):
+    ctx.set_option(2, variant)
+    out = ctx.fingerprint_batch(segs)
+    if ref is None:
+        ref = out
+    agree = sum(int(np.sum(a == b)) for a, b in zip(out, ref))
+    total = sum(a.size for a in ref)
+    assert agree >= 0.99 * total, (variant, agree, total)
+ctx.set_option(2, 0)
+st = np.stack([segs[5], segs[5]], axis=1).reshape(-1)
+ctx.fingerprint_batch([st], channels=2)
+p = engine.match_params(include_endings=True, min_opening_ns=3_000_000_000, min_ending_ns=2_000_000_000)
+res = ctx.analyze_search([segs[6], segs[5], segs[6], segs[7], segs[5], segs[7]], 1, None, synth.HASH_DURATION_NS, p)
+# match: general and fast kernels, small season with planted runs
+season = synth.make_hash_season(4, 700, 300, seed=2, run_len=200)
+for params in (engine.match_params(include_endings=True),
+               engine.match_params(include_endings=True, min_opening_ns=0, min_ending_ns=10 ** 9, threshold=12)):
+    runs = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, params)
+    ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
+print("sanitize target ok", len(runs), res[:1])
