@@ -81,7 +81,11 @@ enum {
     NB200_OPT_FORCE_GENERAL_MATCH = 1,
     /* NB200_OPT_K1_VARIANT: 0 = one warp per FFT frame; 4, 5, 6 = four warps per frame with
      * that many frames in flight per CTA.  Same results; a tuning switch. */
-    NB200_OPT_K1_VARIANT = 2
+    NB200_OPT_K1_VARIANT = 2,
+    /* NB200_OPT_MATCH_DENSE (0|1): the fast match kernel normally tests 4 sampled rows of
+     * every 32-row word and verifies the words that pass; 1 makes it evaluate all 32 cells
+     * of every word (the POPC-roofline kernel).  Results are identical. */
+    NB200_OPT_MATCH_DENSE = 3
 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 

@@ -26,6 +26,7 @@ ERR_STATE = 9
 ERR_COMPARATOR_MINIMUM_PATHS = 10
 OPT_FORCE_GENERAL_MATCH = 1
 OPT_K1_VARIANT = 2
+OPT_MATCH_DENSE = 3
 
 
 class Nb200Error(RuntimeError):

@@ -190,6 +190,9 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
     case NB200_OPT_FORCE_GENERAL_MATCH:
         ctx->force_general_match = value != 0;
         return NB200_OK;
+    case NB200_OPT_MATCH_DENSE:
+        ctx->match_dense = value != 0;
+        return NB200_OK;
     case NB200_OPT_K1_VARIANT:
         if (value != 0 && (value < 4 || value > 6)) return NB200_ERR_INVALID_ARGUMENT;
         ctx->k1_variant = (int)value;

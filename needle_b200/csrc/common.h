@@ -159,6 +159,7 @@ struct nb200_ctx {
     bool ev_valid[4] = {false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
+    bool match_dense = false;           // fast match kernel evaluates every cell instead of 4 sampled rows per word
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls

@@ -390,6 +390,12 @@ __device__ __noinline__ void coop_long_run(const EmitCtx a, uint32_t problem, in
 // or a duplicate diagonal (u >= m-1 in the last band) can look full without
 // being a run; those are filtered where a full word is reported (rare), so the
 // hot loop has no boundary handling at all.
+//
+// SAMPLED = true goes one step further: "all 32 cells match" implies "the cells of rows
+// 0, 8, 16 and 24 match", so the hot loop tests only those four (1/8 of the POPCs); a
+// word that passes (a real run, or chance: p^4 ~ 4e-7 for random hashes) is then
+// verified on all 32 rows by the warp, one row per lane.  Same runs, bit for bit.
+template <bool SAMPLED>
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const MatchArgs a) {
     __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][MATCH_R];
     __shared__ __align__(16) uint32_t s_dst[MATCH_WARPS][FAST_DST_TILE];
@@ -441,32 +447,56 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
         const int n_steps = min(MATCH_R / 32, (n - r0 + 31) / 32);
         for (int step = 0; step < n_steps; step++) {
             const uint4 *dptr = reinterpret_cast<const uint4 *>(dst_t + (248 + 32 * step - MATCH_C * lane));
-            const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
-            uint32_t dw[40];
-#pragma unroll
-            for (int q = 0; q < 10; q++) {
-                const uint4 v = dptr[q];
-                dw[4 * q + 0] = v.x;
-                dw[4 * q + 1] = v.y;
-                dw[4 * q + 2] = v.z;
-                dw[4 * q + 3] = v.w;
-            }
             int mx[MATCH_C];
 #pragma unroll
             for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
+            if (SAMPLED) {
+                // rows 0, 8, 16, 24 of the word: window elements 8 r + 7 - c, i.e. dw[0..32)
+                uint32_t dw[32];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const uint4 sv = sptr[q];
-                const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
+                for (int q = 0; q < 8; q++) {
+                    const uint4 v = dptr[q];
+                    dw[4 * q + 0] = v.x;
+                    dw[4 * q + 1] = v.y;
+                    dw[4 * q + 2] = v.z;
+                    dw[4 * q + 3] = v.w;
+                }
+                uint32_t sr[4];
 #pragma unroll
-                for (int kk = 0; kk < 4; kk += 2) {
-                    const int k = 4 * q + kk;
+                for (int r = 0; r < 4; r++) sr[r] = src_t[32 * step + 8 * r];
+#pragma unroll
+                for (int r = 0; r < 4; r += 2)
 #pragma unroll
                     for (int c = 0; c < MATCH_C; c++) {
-                        // cell (row k, diagonal c of this lane): window element k + 7 - c
-                        const int p0 = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]);
-                        const int p1 = __popc(s4[kk + 1] ^ dw[k + 1 + (MATCH_C - 1) - c]);
-                        mx[c] = max(mx[c], max(p0, p1));     // one 3-input max per two cells
+                        const int p0 = __popc(sr[r] ^ dw[8 * r + (MATCH_C - 1) - c]);
+                        const int p1 = __popc(sr[r + 1] ^ dw[8 * (r + 1) + (MATCH_C - 1) - c]);
+                        mx[c] = max(mx[c], max(p0, p1));
+                    }
+            } else {
+                const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
+                uint32_t dw[40];
+#pragma unroll
+                for (int q = 0; q < 10; q++) {
+                    const uint4 v = dptr[q];
+                    dw[4 * q + 0] = v.x;
+                    dw[4 * q + 1] = v.y;
+                    dw[4 * q + 2] = v.z;
+                    dw[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const uint4 sv = sptr[q];
+                    const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk += 2) {
+                        const int k = 4 * q + kk;
+#pragma unroll
+                        for (int c = 0; c < MATCH_C; c++) {
+                            // cell (row k, diagonal c of this lane): window element k + 7 - c
+                            const int p0 = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]);
+                            const int p1 = __popc(s4[kk + 1] ^ dw[k + 1 + (MATCH_C - 1) - c]);
+                            mx[c] = max(mx[c], max(p0, p1));     // one 3-input max per two cells
+                        }
                     }
                 }
             }
@@ -492,6 +522,12 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                     int jm = (i0 - 1 - u) % M;                              // j0 - 1
                     if (jm < 0) jm += M;
                     if (jm + 31 > M - 1) continue;                          // the wrap point is inside the word
+                    if (SAMPLED) {
+                        // the four sampled rows matched: now all 32, one row per lane
+                        const int s0 = 248 + 32 * step - MATCH_C * src_lane + (MATCH_C - 1) - c;   // row 0's dst slot
+                        const bool ok = __popc(src_t[32 * step + lane] ^ dst_t[s0 + lane]) <= T;
+                        if (__ballot_sync(0xffffffffu, ok) != 0xffffffffu) continue;
+                    }
                     coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
                 }
             }
@@ -744,8 +780,10 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         uint32_t grid = (uint32_t)ctx->sm_count * 4;
         grid = std::min<uint32_t>(grid, (warps_needed + MATCH_WARPS - 1) / MATCH_WARPS);
         NB_CUDA_F(cudaEventRecord(ctx->ev[4], s));
-        if (fast)
-            match_fast_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        if (fast && ctx->match_dense)
+            match_fast_kernel<false><<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        else if (fast)
+            match_fast_kernel<true><<<grid, MATCH_WARPS * 32, 0, s>>>(args);
         else
             match_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
         NB_CUDA_F(cudaGetLastError());

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
+from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, OPT_MATCH_DENSE, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -27,12 +27,14 @@ def check_season(ctx, orc, season, vote=True, **kw):
         want_results, want_rows = None, H.oracle_pair_runs(orc, season, **kw)
     runs = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, p)
     assert H.runs_as_rows(runs) == want_rows
-    # the general kernel gives the same list where the fast variant was eligible
-    ctx.set_option(OPT_FORCE_GENERAL_MATCH, 1)
-    try:
-        assert np.array_equal(ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, p), runs)
-    finally:
-        ctx.set_option(OPT_FORCE_GENERAL_MATCH, 0)
+    # the same list from the other kernels that could have been chosen: the exhaustive fast
+    # kernel (every cell instead of 4 sampled rows per word) and the general kernel
+    for opt in (OPT_MATCH_DENSE, OPT_FORCE_GENERAL_MATCH):
+        ctx.set_option(opt, 1)
+        try:
+            assert np.array_equal(ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, p), runs)
+        finally:
+            ctx.set_option(opt, 0)
     # device-resident path gives the same answer
     hs = engine.HashSet.upload(ctx, season.hashes, season.ts_ns, season.seg_offset)
     rs = hs.match(p)
@@ -123,6 +125,27 @@ def test_fast_kernel_word_ownership(ctx, oracle):
     assert len(runs) >= 15
     runs, _ = check_season(ctx, oracle, season, threshold=0, min_opening_ns=16_000_000_000)    # lcand 66
     assert len(runs) >= 20
+
+
+def test_sampled_rows_false_positives(ctx, oracle):
+    """Hashes that match on rows 0, 8, 16, 24 of many words but not in between (period-8
+    pattern): every such word passes the sampled filter and must be rejected by the
+    32-row verification; plus genuine long runs."""
+    rng = np.random.default_rng(31)
+    n = 1200
+    a = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    key = np.uint32(0x5A5A1234)
+    a[::8] = key                      # every 8th hash identical in both videos, all others random
+    b[::8] = key
+    c = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    c[100:400] = a[300:600]           # a genuine 300-run between videos 0 and 2
+    ts = synth.hash_timestamps(2 * n, 2)[:n]
+    none = (np.zeros(0, np.uint32), np.zeros(0, np.uint64))
+    season = H.season_from_lists([(a, ts), (b, ts), (c, ts)], [none] * 3)
+    runs, _ = check_season(ctx, oracle, season, threshold=0)
+    assert len(runs) == 1 and int(runs[0]["len"]) >= 299
+    check_season(ctx, oracle, season, threshold=10)
 
 
 def test_threshold_extremes(ctx, oracle):

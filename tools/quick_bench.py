@@ -11,18 +11,23 @@ for n_videos in (28, 60, 120):
     season = synth.make_hash_season(n_videos, 2897, 1443, seed=1)
     hs = engine.HashSet.upload(ctx, season.hashes, season.ts_ns, season.seg_offset)
     p = engine.match_params(include_endings=True)
-    for _ in range(3):
-        rs = hs.match(p)
-    ts = []
-    for _ in range(5):
-        t0 = time.perf_counter(); rs = hs.match(p); t1 = time.perf_counter()
-        ms = ctx.last_kernel_ms()
-        ts.append((ms["match"], ms["simhash"], (t1 - t0) * 1e3))
-    n_runs, cells = rs.count()
-    k = min(t[0] for t in ts)
-    out["match_%d" % n_videos] = dict(pairs=n_videos * (n_videos - 1) // 2, cells=cells, runs=n_runs,
-                                      kernel_ms=k, simhash_ms=min(t[1] for t in ts), wall_ms=min(t[2] for t in ts),
-                                      Tcells_per_s=cells / k / 1e9)
+    for name, opt in (("sampled", None), ("dense", 3), ("general", 1)):
+        if opt:
+            ctx.set_option(opt, 1)
+        for _ in range(3):
+            rs = hs.match(p)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter(); rs = hs.match(p); t1 = time.perf_counter()
+            ms = ctx.last_kernel_ms()
+            ts.append((ms["match"], ms["simhash"], (t1 - t0) * 1e3))
+        if opt:
+            ctx.set_option(opt, 0)
+        n_runs, cells = rs.count()
+        k = min(t[0] for t in ts)
+        out["match_%d_%s" % (n_videos, name)] = dict(
+            pairs=n_videos * (n_videos - 1) // 2, cells=cells, runs=n_runs, kernel_ms=k,
+            simhash_ms=min(t[1] for t in ts), wall_ms=min(t[2] for t in ts), Tcells_per_s=cells / k / 1e9)
 # fingerprint: 28 x 20 min (opening 50% + ending 25%)
 rng = np.random.default_rng(0)
 segs = []
