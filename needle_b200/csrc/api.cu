@@ -519,15 +519,28 @@ int nb200_runset_download(nb200_ctx *ctx, const nb200_runset *rs, nb200_run *run
     NB_CUDA(cudaMemcpyAsync(ctx->h_runs.p, rs->d_runs.p, rs->n_runs * sizeof(DeviceRun),
                             cudaMemcpyDeviceToHost, ctx->stream));
     NB_CUDA(cudaStreamSynchronize(ctx->stream));
-    DeviceRun *tmp_begin = ctx->h_runs.as<DeviceRun>();
-    std::vector<DeviceRun> tmp(tmp_begin, tmp_begin + rs->n_runs);
-    // the reference's push order: pair, opening before ending, i desc, j desc
-    // (problems are numbered in (pair, is_ending) order)
-    std::sort(tmp.begin(), tmp.end(), [](const DeviceRun &a, const DeviceRun &b) {
-        if (a.problem != b.problem) return a.problem < b.problem;
-        if (a.i_end != b.i_end) return a.i_end > b.i_end;
-        return a.j_end > b.j_end;
-    });
+    // the reference's push order: pair, opening before ending, i desc, j desc (problems are
+    // numbered in (pair, is_ending) order).  Bucket by problem, then order each small bucket.
+    const DeviceRun *src = ctx->h_runs.as<DeviceRun>();
+    const size_t n_problems = rs->problem_pair.size();
+    std::vector<uint64_t> bucket(n_problems + 1, 0);
+    for (uint64_t k = 0; k < rs->n_runs; k++) {
+        if (src[k].problem >= n_problems) return NB200_ERR_STATE;
+        bucket[src[k].problem + 1]++;
+    }
+    for (size_t q = 0; q < n_problems; q++) bucket[q + 1] += bucket[q];
+    std::vector<DeviceRun> tmp(rs->n_runs);
+    {
+        std::vector<uint64_t> cursor(bucket.begin(), bucket.end() - 1);
+        for (uint64_t k = 0; k < rs->n_runs; k++) tmp[cursor[src[k].problem]++] = src[k];
+    }
+    for (size_t q = 0; q < n_problems; q++)
+        if (bucket[q + 1] - bucket[q] > 1)
+            std::sort(tmp.begin() + (long)bucket[q], tmp.begin() + (long)bucket[q + 1],
+                      [](const DeviceRun &a, const DeviceRun &b) {
+                          if (a.i_end != b.i_end) return a.i_end > b.i_end;
+                          return a.j_end > b.j_end;
+                      });
     for (uint64_t k = 0; k < rs->n_runs; k++) {
         const DeviceRun &r = tmp[k];
         nb200_run &o = runs_out[k];

@@ -391,10 +391,10 @@ __device__ __noinline__ void coop_long_run(const EmitCtx a, uint32_t problem, in
 // being a run; those are filtered where a full word is reported (rare), so the
 // hot loop has no boundary handling at all.
 //
-// SAMPLED = true goes one step further: "all 32 cells match" implies "the cells of rows
-// 0, 8, 16 and 24 match", so the hot loop tests only those four (1/8 of the POPCs); a
-// word that passes (a real run, or chance: p^4 ~ 4e-7 for random hashes) is then
-// verified on all 32 rows by the warp, one row per lane.  Same runs, bit for bit.
+// SAMPLED = true goes one step further: "all 32 cells match" implies "the cells of any
+// 4 rows match", so the word is tested 4 rows at a time and abandoned (by the whole
+// warp) as soon as no diagonal survives -- usually after the first 4 rows, 1/8 of the
+// POPCs.  Survivors of all 8 stages are exactly the full words.  Same runs, bit for bit.
 template <bool SAMPLED>
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const MatchArgs a) {
     __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][MATCH_R];
@@ -451,27 +451,45 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
 #pragma unroll
             for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
             if (SAMPLED) {
-                // rows 0, 8, 16, 24 of the word: window elements 8 r + 7 - c, i.e. dw[0..32)
-                uint32_t dw[32];
+                // Adaptive depth.  Stage s tests rows o, o+8, o+16, o+24 with o = bitrev3(s)
+                // (0,4,2,6,1,5,3,7): 4 more rows of every word.  The warp leaves as soon as no
+                // lane has a diagonal that still matches everywhere it was tested: one stage
+                // for unrelated hashes (p^4 ~ 4e-7), a few for correlated audio; a diagonal
+                // that survives all 8 stages has 32 matching cells.
+                uint32_t dw[40];
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
+                for (int q = 0; q < 10; q++) {
                     const uint4 v = dptr[q];
                     dw[4 * q + 0] = v.x;
                     dw[4 * q + 1] = v.y;
                     dw[4 * q + 2] = v.z;
                     dw[4 * q + 3] = v.w;
                 }
-                uint32_t sr[4];
+                bool alive = true;
 #pragma unroll
-                for (int r = 0; r < 4; r++) sr[r] = src_t[32 * step + 8 * r];
+                for (int stage = 0; stage < 8; stage++) {
+                    if (alive) {
+                        const int o = ((stage & 1) << 2) | (stage & 2) | ((stage & 4) >> 2);
+                        uint32_t sr[4];
 #pragma unroll
-                for (int r = 0; r < 4; r += 2)
+                        for (int r = 0; r < 4; r++) sr[r] = src_t[32 * step + o + 8 * r];
 #pragma unroll
-                    for (int c = 0; c < MATCH_C; c++) {
-                        const int p0 = __popc(sr[r] ^ dw[8 * r + (MATCH_C - 1) - c]);
-                        const int p1 = __popc(sr[r + 1] ^ dw[8 * (r + 1) + (MATCH_C - 1) - c]);
-                        mx[c] = max(mx[c], max(p0, p1));
+                        for (int r = 0; r < 4; r += 2)
+#pragma unroll
+                            for (int c = 0; c < MATCH_C; c++) {
+                                const int p0 = __popc(sr[r] ^ dw[o + 8 * r + (MATCH_C - 1) - c]);
+                                const int p1 = __popc(sr[r + 1] ^ dw[o + 8 * (r + 1) + (MATCH_C - 1) - c]);
+                                mx[c] = max(mx[c], max(p0, p1));
+                            }
+                        if (stage < 7) {
+                            int b2 = mx[0];
+#pragma unroll
+                            for (int c = 1; c < MATCH_C; c++) b2 = min(b2, mx[c]);
+                            alive = __any_sync(0xffffffffu, b2 <= T);
+                        }
                     }
+                }
+                if (!alive) continue;   // warp-uniform: nothing survived
             } else {
                 const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
                 uint32_t dw[40];
@@ -522,12 +540,6 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                     int jm = (i0 - 1 - u) % M;                              // j0 - 1
                     if (jm < 0) jm += M;
                     if (jm + 31 > M - 1) continue;                          // the wrap point is inside the word
-                    if (SAMPLED) {
-                        // the four sampled rows matched: now all 32, one row per lane
-                        const int s0 = 248 + 32 * step - MATCH_C * src_lane + (MATCH_C - 1) - c;   // row 0's dst slot
-                        const bool ok = __popc(src_t[32 * step + lane] ^ dst_t[s0 + lane]) <= T;
-                        if (__ballot_sync(0xffffffffu, ok) != 0xffffffffu) continue;
-                    }
                     coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
                 }
             }
