@@ -282,6 +282,15 @@ int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t 
                                uint64_t delay_ns, uint64_t item_ns, const uint64_t *seek_to_ns,
                                void *d_hashes_out, void *d_ts_ns_out, uint64_t capacity);
 
+/* Fills in the timestamps of stored hashes from their index alone,
+ *   ts[k] = delay + item.mul_f32((k * stride) as f32) + seek_to   (analyzer.rs:309,314-318),
+ * for n_segments segments of seg_len[s] elements at element dev_offset[s] of d_ts_ns.
+ * Asynchronous on the context's stream.  A rank of a multi-GPU job regenerates the
+ * timestamps of every segment this way instead of receiving them. */
+int nb200_timestamps_fill(nb200_ctx *ctx, void *d_ts_ns, const uint64_t *dev_offset, const uint64_t *seg_len,
+                          const uint64_t *seek_to_ns, uint32_t n_segments, uint32_t stride, uint64_t delay_ns,
+                          uint64_t item_ns);
+
 /* nb200_pcmset_upload + nb200_fingerprint_run_into in one call for MONO host PCM
  * (pinned for full rate): the H2D copy runs in chunks on a second stream while K1
  * already works on the chunks that have landed.  n_segments must be even. */

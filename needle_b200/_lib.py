@@ -119,6 +119,7 @@ PROTOTYPES = {
     "nb200_fingerprint_run": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _PP]),
     "nb200_fingerprint_layout": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _U64P]),
     "nb200_fingerprint_run_into": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P, C.c_uint64]),
+    "nb200_timestamps_fill": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64]),
     "nb200_fingerprint_host_into": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _P,
                                               _P, _P, C.c_uint64]),
     "nb200_fingerprint_batch": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P]),

@@ -164,7 +164,8 @@ struct nb200_ctx {
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
-    nb200::PinnedBuf h_stage, h_small, h_runs;
+    nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
+    nb200::DevBuf d_tsfill;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;

@@ -694,6 +694,21 @@ __global__ void __launch_bounds__(K2_TILE) fp_classify_kernel(const K2Args a) {
     }
 }
 
+// Timestamps of stored hashes are a function of the index alone (analyzer.rs:309,314-318):
+// ts[k] = delay + item.mul_f32((k * stride) as f32) + seek_to.  Every rank of a multi-GPU job
+// can therefore fill them in for ALL segments itself instead of exchanging 8 bytes per hash.
+struct TsSegment {
+    uint64_t dev_offset, len, seek_to_ns;
+};
+__global__ void ts_fill_kernel(uint64_t *__restrict__ ts, const TsSegment *__restrict__ segs, uint32_t stride,
+                               float item_secs, uint64_t delay_ns) {
+    const TsSegment sg = segs[blockIdx.y];
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sg.len) return;
+    const float p = __fmul_rn(__ull2float_rn(k * stride), item_secs);
+    ts[sg.dev_offset + k] = delay_ns + __double2ull_rn((double)p * 1e9) + sg.seek_to_ns;
+}
+
 // (L + R) / 2 with C integer division, as Chromaprint's AudioProcessor::LoadStereo
 __global__ void downmix_kernel(const int16_t *__restrict__ stereo, int16_t *__restrict__ mono, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1140,6 +1155,33 @@ int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t 
     NB_TRY(fingerprint_run_pipelined(ctx, ps, nullptr, stride, delay_ns, item_ns, seek_to_ns, &hs,
                                      d_hashes_out, d_ts_ns_out, capacity));
     nb200_hashset_free(hs);   // borrowed arrays: nothing is released
+    return NB200_OK;
+}
+
+int nb200_timestamps_fill(nb200_ctx *ctx, void *d_ts_ns, const uint64_t *dev_offset, const uint64_t *seg_len,
+                          const uint64_t *seek_to_ns, uint32_t n_segments, uint32_t stride, uint64_t delay_ns,
+                          uint64_t item_ns) {
+    if (!ctx || !d_ts_ns || !dev_offset || !seg_len) return NB200_ERR_NULL_ARGUMENT;
+    if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;
+    if (n_segments == 0) return NB200_OK;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n_segments * sizeof(TsSegment);
+    NB_TRY(ctx->h_tsfill.reserve(bytes));
+    NB_TRY(ctx->d_tsfill.reserve(bytes));
+    // the pinned staging may still be in flight from the previous call on this stream
+    NB_CUDA(cudaEventSynchronize(ctx->ev_chunk[6]));
+    TsSegment *tab = ctx->h_tsfill.as<TsSegment>();
+    uint64_t max_len = 1;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        tab[s] = {dev_offset[s], seg_len[s], seek_to_ns ? seek_to_ns[s] : 0};
+        max_len = std::max(max_len, seg_len[s]);
+    }
+    NB_CUDA(cudaMemcpyAsync(ctx->d_tsfill.p, tab, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    NB_CUDA(cudaEventRecord(ctx->ev_chunk[6], ctx->stream));
+    ts_fill_kernel<<<dim3((unsigned)((max_len + 255) / 256), n_segments), 256, 0, ctx->stream>>>(
+        (uint64_t *)d_ts_ns, ctx->d_tsfill.as<TsSegment>(), stride, as_secs_f32(item_ns), delay_ns);
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
     return NB200_OK;
 }
 

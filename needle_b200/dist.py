@@ -185,9 +185,12 @@ class GpuBackend:
         self.ctx.fingerprint_host_into(segments, ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
                                        stride=plan.stride, seek_to_ns=seek_to_ns)
 
-    def exchange(self, dist, ex, group=None):
+    def exchange(self, dist, ex, plan: SeasonPlan, seek_to_ns, group=None):
+        """ONE collective: the hashes.  Timestamps are a function of the index
+        (analyzer.rs:309), so every rank fills in all of them itself."""
         dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
-        dist.all_gather_into_tensor(ex["ts_recv"], ex["ts_send"], group=group)
+        self.ctx.timestamps_fill(ex["ts_recv"].data_ptr(), plan.dev_offset, plan.seg_len, seek_to_ns,
+                                 stride=plan.stride)
 
     def season_from_gathered(self, ex, plan: SeasonPlan, world: int):
         h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])
@@ -343,7 +346,7 @@ class SeasonJob:
     def _after_fingerprint(self, ex, t):
         b = self.backend
         if self.world > 1:
-            b.exchange(self.dist, ex, self.group)
+            b.exchange(self.dist, ex, self.plan, self.seek_to_ns, self.group)
         season = b.season_from_gathered(ex, self.plan, self.world)
         t = self._tick("exchange_enqueue", t)
         start, end = self.slices[self.rank]

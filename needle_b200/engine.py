@@ -156,6 +156,15 @@ class Context:
                                                 C.c_void_p(d_hashes), C.c_void_p(d_ts_ns), capacity),
               "nb200_fingerprint_host_into")
 
+    def timestamps_fill(self, d_ts_ns: int, dev_offset, seg_len, seek_to_ns, stride: int = 2,
+                        delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS):
+        """nb200_timestamps_fill: timestamps of stored hashes from their index (asynchronous)."""
+        do = np.ascontiguousarray(dev_offset, dtype=np.uint64)
+        ln = np.ascontiguousarray(seg_len, dtype=np.uint64)
+        sk = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        check(lib().nb200_timestamps_fill(self._h, C.c_void_p(d_ts_ns), ptr(do), ptr(ln), ptr(sk), ln.size, stride,
+                                          delay_ns, item_ns), "nb200_timestamps_fill")
+
     def analyze_search(self, segments, channels, seek_to_ns, hash_duration_ns, params: MatchParams):
         """nb200_analyze_search: segments = [opening_0, ending_0, opening_1, ...] PCM arrays."""
         segs = [np.ascontiguousarray(s, dtype=np.int16).reshape(-1) for s in segments]

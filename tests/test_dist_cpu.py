@@ -82,9 +82,12 @@ class OracleBackend:
             hv[o:o + n] = h
             tv[o:o + n] = t
 
-    def exchange(self, dist, ex, group=None):
+    def exchange(self, dist, ex, plan, seek_to_ns, group=None):
         dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
-        dist.all_gather_into_tensor(ex["ts_recv"], ex["ts_send"], group=group)
+        tv = ex["ts_recv"].numpy().view(np.uint64)      # timestamps from the index, like nb200_timestamps_fill
+        for s in range(2 * plan.n_videos):
+            n, a = int(plan.seg_len[s]), int(plan.dev_offset[s])
+            tv[a:a + n] = synth.hash_timestamps(n * plan.stride, plan.stride, seek_to_ns=int(seek_to_ns[s]))[:n]
 
     def season_from_gathered(self, ex, plan, world):
         h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])

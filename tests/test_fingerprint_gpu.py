@@ -199,6 +199,12 @@ def test_fingerprint_into_and_hashset_view(ctx):
         a, n = int(doff[k]), int(dlen[k])
         assert np.array_equal(hv[a:a + n], h[int(off[k]):int(off[k + 1])])
         assert np.array_equal(tv[a:a + n], t[int(off[k]):int(off[k + 1])])
+    # the timestamps are a function of the index: nb200_timestamps_fill reproduces K2's
+    tf = torch.zeros(total + 8, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.timestamps_fill(tf.data_ptr(), doff, dlen, seek, stride=2)
+    ctx.synchronize()
+    assert np.array_equal(tf.cpu().numpy().view(np.uint64), tv)
     with pytest.raises(Nb200Error):
         ps.fingerprint_into(hb.data_ptr(), tb.data_ptr(), total - 4, stride=2, seek_to_ns=seek)   # too small
     p = engine.match_params(include_endings=True)
