@@ -296,7 +296,10 @@ def run_b200(args):
         _season = backend.season_from_gathered(job._buffers(), job.plan, world)   # filled by the run above
         n_runs_local = backend.match(_season, params, my_pairs).shape[0]
         _season.free()
-    d2h_bytes = 24 * n_runs_local + 16 + (8 * int(sl.sum()) if rank == 0 else 0)
+    if world == 1:
+        d2h_bytes = 48 * n_videos + 16 + 16    # the result table, the vote's flags, the match counters
+    else:
+        d2h_bytes = 64 * n_runs_local + 16     # this rank's runs (they carry their timestamps) + counters
 
     # bring the clocks up before anything is timed (idle parts sit at 120 MHz)
     t_spin = time.perf_counter()
@@ -304,7 +307,7 @@ def run_b200(args):
         job.run_resident(pcmset)
 
     sampler = ClockSampler(local_rank)
-    kernel_ms = {"fp_fft_chroma": 0.0, "fp_classify": 0.0, "match": 0.0, "simhash": 0.0}
+    kernel_ms = {"fp_fft_chroma": 0.0, "fp_classify": 0.0, "match": 0.0, "simhash": 0.0, "vote": 0.0}
 
     # ---- value: inputs resident in HBM
     for _ in range(max(args.warmup, 3)):

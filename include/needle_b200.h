@@ -73,6 +73,9 @@ int nb200_ctx_synchronize(nb200_ctx *ctx);
  * [2] match K3, [3] simhash K4.  Counters of launches since context creation
  * in n_launches (may be NULL). */
 int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches);
+/* Milliseconds of the device vote kernels (group, heap replay, find_best_match) of the
+ * last search; 0 when the host voted. */
+int nb200_ctx_last_vote_ms(nb200_ctx *ctx, float *ms);
 
 /* Tuning / test switches.  NB200_OPT_FORCE_GENERAL_MATCH (value 0|1): always run
  * the general match kernel, also where the fast variant (all candidate run
@@ -85,7 +88,13 @@ enum {
     /* NB200_OPT_MATCH_DENSE (0|1): the fast match kernel normally tests 4 sampled rows of
      * every 32-row word and verifies the words that pass; 1 makes it evaluate all 32 cells
      * of every word (the POPC-roofline kernel).  Results are identical. */
-    NB200_OPT_MATCH_DENSE = 3
+    NB200_OPT_MATCH_DENSE = 3,
+    /* NB200_OPT_HOST_VOTE (0|1): nb200_search* / nb200_analyze_search normally replay the
+     * heaps and run find_best_match on the device (vote_device.cu) and download only the
+     * per-video results; 1 downloads the runs and votes on the host (vote.cpp) instead.
+     * Results are identical; the host vote is also the automatic fallback when a table
+     * has more runs, or a video more candidates, than the device kernels are sized for. */
+    NB200_OPT_HOST_VOTE = 4
 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 
@@ -168,7 +177,8 @@ int nb200_match_pairs(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts
                       const nb200_match_params *params, nb200_run **out_runs, uint64_t *out_n);
 
 /* Comparator::run_with_frame_hashes: match every pair on the GPU, then replay
- * the reference's BinaryHeap pushes and find_best_match on the host.
+ * the reference's BinaryHeap pushes and find_best_match (on the device too, unless
+ * NB200_OPT_HOST_VOTE; identical results).
  * hash_duration_ns[n_videos] = FrameHashes::hash_duration per video.
  * results[n_videos]. */
 int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
@@ -331,6 +341,12 @@ int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64
                          int channels, uint32_t n_videos, const uint64_t *seek_to_ns,
                          uint64_t hash_duration_ns, const nb200_match_params *params,
                          nb200_search_result *results);
+/* The same on PCM that is already in HBM (nb200_pcmset_upload; 2 segments per video):
+ * K1, K2, match, simhash and the vote are enqueued back to back on the context's
+ * stream, the host waits once and downloads 48 bytes per video. */
+int nb200_pcmset_search(nb200_ctx *ctx, const nb200_pcmset *ps, const uint64_t *seek_to_ns,
+                        uint64_t hash_duration_ns, const nb200_match_params *params,
+                        nb200_search_result *results);
 
 /* ------------------------------------------------------------ persistence */
 

@@ -27,6 +27,7 @@ ERR_COMPARATOR_MINIMUM_PATHS = 10
 OPT_FORCE_GENERAL_MATCH = 1
 OPT_K1_VARIANT = 2
 OPT_MATCH_DENSE = 3
+OPT_HOST_VOTE = 4
 
 
 class Nb200Error(RuntimeError):
@@ -87,6 +88,7 @@ PROTOTYPES = {
     "nb200_ctx_host_profile": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "nb200_ctx_synchronize": (C.c_int, [_P]),
     "nb200_ctx_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float), _U64P]),
+    "nb200_ctx_last_vote_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "nb200_host_alloc": (C.c_int, [_PP, C.c_size_t]),
     "nb200_host_free": (C.c_int, [_P]),
     "nb200_free": (None, [_P]),
@@ -134,6 +136,7 @@ PROTOTYPES = {
     "nb200_fp_get_raw": (C.c_int, [_P, _PP, C.POINTER(C.c_size_t)]),
     "nb200_analyze_search": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, _P, C.c_uint64,
                                        C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
+    "nb200_pcmset_search": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
     "nb200_framehashes_write": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, _P, _P, C.c_uint64,
                                           C.c_uint64, C.c_char_p]),
     "nb200_framehashes_read": (C.c_int, [C.c_char_p, _PP, _PP, _U64P, _PP, _PP, _U64P, _U64P,

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libneedle_b200.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 
-SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote.cpp", "persist.cpp"]
+SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote_device.cu", "vote.cpp", "persist.cpp"]
 HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"),
            os.path.join(INCLUDE, "needle_b200.h")]
 

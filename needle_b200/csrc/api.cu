@@ -150,7 +150,7 @@ int nb200_ctx_create(int device, nb200_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int k = 0; ok && k < 8; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+    for (int k = 0; ok && k < 10; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
     for (int k = 0; ok && k < 8; k++)
         ok = cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && ctx->h_small.reserve(256) == NB200_OK;
@@ -168,10 +168,10 @@ void nb200_ctx_destroy(nb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 10; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    for (int k = 0; k < 8; k++)
         if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]);
-    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -192,6 +192,9 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
         return NB200_OK;
     case NB200_OPT_MATCH_DENSE:
         ctx->match_dense = value != 0;
+        return NB200_OK;
+    case NB200_OPT_HOST_VOTE:
+        ctx->host_vote = value != 0;
         return NB200_OK;
     case NB200_OPT_K1_VARIANT:
         if (value != 0 && (value < 4 || value > 6)) return NB200_ERR_INVALID_ARGUMENT;
@@ -225,6 +228,14 @@ int nb200_ctx_last_kernel_ms(nb200_ctx *ctx, float ms[4], uint64_t *n_launches) 
         if (ctx->ev_valid[k]) NB_CUDA(cudaEventElapsedTime(&ms[k], ctx->ev[2 * k], ctx->ev[2 * k + 1]));
     }
     if (n_launches) *n_launches = ctx->n_launches;
+    return NB200_OK;
+}
+
+int nb200_ctx_last_vote_ms(nb200_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return NB200_ERR_NULL_ARGUMENT;
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *ms = 0.f;
+    if (ctx->ev_valid[4]) NB_CUDA(cudaEventElapsedTime(ms, ctx->ev[8], ctx->ev[9]));
     return NB200_OK;
 }
 
@@ -610,11 +621,10 @@ int nb200_search(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
                  const nb200_match_params *params, nb200_search_result *results) {
     if (!ctx || !seg_offset || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
     if (n_videos < 2) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;   // main.rs:305-315, capi lib.rs:569
-    nb200_run *runs = nullptr;
-    uint64_t n_runs = 0;
-    NB_TRY(nb200_match_pairs(ctx, hashes, ts_ns, seg_offset, n_videos, nullptr, 0, params, &runs, &n_runs));
-    int st = vote_impl(hash_duration_ns, n_videos, nullptr, 0, params, runs, n_runs, nullptr, results);
-    free(runs);
+    nb200_hashset *hs = nullptr;
+    NB_TRY(nb200_hashset_upload(ctx, hashes, ts_ns, seg_offset, n_videos, &hs));
+    const int st = nb200_search_hashset(ctx, hs, hash_duration_ns, params, results);
+    nb200_hashset_free(hs);
     return st;
 }
 
@@ -625,6 +635,34 @@ int nb200_search_hashset(nb200_ctx *ctx, const nb200_hashset *hs, const uint64_t
                          const nb200_match_params *params, nb200_search_result *results) {
     if (!ctx || !hs || !hash_duration_ns || !params || !results) return NB200_ERR_NULL_ARGUMENT;
     if (hs->n_videos < 2) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;
+    ctx->ev_valid[4] = false;
+    if (!ctx->host_vote) {
+        // everything stays on the device; ONE synchronisation, then 48 bytes per video come back
+        MatchPending mp;
+        uint32_t cap_min = 0;
+        for (int attempt = 0;; attempt++) {
+            NB_TRY(match_enqueue(ctx, hs, nullptr, 0, params, 0, cap_min, &mp));
+            {
+                PhaseTimer pt(ctx, NB200_PHASE_VOTE);
+                NB_TRY(vote_enqueue(ctx, ctx->d_runs.as<DeviceRun>(), ctx->d_counters.as<unsigned int>() + 1, mp.run_cap,
+                                    hash_duration_ns, hs->n_videos, nullptr, 0, params));
+            }
+            PhaseTimer pt(ctx, NB200_PHASE_MATCH);
+            uint64_t n_runs = 0;
+            NB_TRY(match_collect(ctx, mp, &n_runs));
+            if (n_runs <= mp.run_cap) break;
+            if (attempt == 1 || n_runs > 0x7ffffff0ull) return NB200_ERR_TOO_LARGE;
+            cap_min = (uint32_t)n_runs;
+        }
+        const size_t b_res = (size_t)hs->n_videos * sizeof(nb200_search_result);
+        uint32_t flags[4];
+        memcpy(flags, ctx->h_results.as<char>() + b_res, sizeof(flags));
+        if (!(flags[0] & VOTE_FLAG_FALLBACK)) {
+            memcpy(results, ctx->h_results.p, b_res);
+            return (flags[0] & VOTE_FLAG_UNDERFLOW) ? NB200_ERR_DURATION_UNDERFLOW : NB200_OK;
+        }
+        // a table or a video beyond the device vote's bounds: fall through to the host vote
+    }
     nb200_runset *rs = nullptr;
     NB_TRY(nb200_match_run(ctx, hs, nullptr, 0, params, &rs));
     std::vector<nb200_run> runs(std::max<uint64_t>(rs->n_runs, 1));

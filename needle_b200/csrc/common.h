@@ -154,17 +154,26 @@ struct nb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;     // the one in use (own or caller's)
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[8] = {};            // pairs: K1, K2, K3, K4
+    cudaEvent_t ev[10] = {};           // pairs: K1, K2, K3, K4, device vote
     cudaEvent_t ev_chunk[8] = {};      // H2D chunk landed (pipelined analyze)
-    bool ev_valid[4] = {false, false, false, false};
+    bool ev_valid[5] = {false, false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
     bool match_dense = false;           // fast match kernel evaluates every cell instead of 4 sampled rows per word
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
+    bool host_vote = false;             // searches download the runs and vote on the host (vote.cpp) instead of on the device
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
+    nb200::DevBuf d_problems_g, d_tile_end_g, d_lut_g;   // the general kernel's tiling of the same problems
     nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
+    nb200::PinnedBuf h_fp_stage, h_vote_stage, h_results;   // one staging area per phase: nothing waits for a copy to drain
+    // device vote scratch (vote_device.cu)
+    nb200::DevBuf d_vote_groups, d_vote_order, d_vote_csr, d_vote_hd, d_vote_results, d_vote_flags, d_vote_scan_tmp,
+        d_vote_gather;
+    std::vector<uint32_t> vote_csr_host;   // cached CSR of the default pair list
+    uint32_t vote_csr_videos = 0;          // n_videos the cache was built for (0: none)
+    bool vote_csr_on_device = false;
     nb200::DevBuf d_tsfill;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
@@ -218,15 +227,45 @@ struct PhaseTimer {
 };
 
 // match.cu ---------------------------------------------------------------
-struct DeviceRun {
+struct DeviceRun {   // 64 bytes
     uint32_t problem;
     uint32_t i_end, j_end, len;
     uint32_t src_simhash, dst_simhash;
+    uint32_t group;      // 2 * (global pair index) + is_ending; stamped by the simhash kernel
+    uint32_t reserved;
     uint64_t src_start_ns, src_end_ns, dst_start_ns, dst_end_ns;
 };
+static_assert(sizeof(DeviceRun) == 64, "DeviceRun is exchanged between ranks as raw bytes");
 
+// What match_enqueue left on ctx's stream and in ctx's scratch (d_runs, d_counters):
+// nothing has been waited for.  counters[1] = number of runs found (may exceed
+// run_cap: then only run_cap were stored and the caller re-runs with more room),
+// counters[2] bit 0 = a Duration subtraction would have underflowed.
+struct MatchPending {
+    uint32_t n_problems = 0;
+    uint32_t run_cap = 0;
+    uint64_t n_cells = 0;
+    std::vector<uint32_t> problem_pair;
+    std::vector<uint8_t> problem_is_ending;
+};
+int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2], uint64_t n_pairs,
+                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out);
+// Waits for the stream and reads the counters: DURATION_UNDERFLOW, or OK with the number of
+// runs found (> run_cap: enqueue again with run_cap_min = that number).
+int match_collect(nb200_ctx *ctx, const MatchPending &mp, uint64_t *n_runs);
 int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
                    uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out);
+
+// vote_device.cu ---------------------------------------------------------
+// Device-side heap replay + find_best_match over runs that are already in HBM.
+// Enqueues on ctx->stream; results land in ctx->h_results (pinned) after the
+// caller synchronises: [n_videos] nb200_search_result, then 4 u32 flags
+// (VOTE_FLAG_*).  d_n_runs points at the device-resident run count.
+constexpr uint32_t VOTE_FLAG_UNDERFLOW = 1u;   // a Duration subtraction would have underflowed
+constexpr uint32_t VOTE_FLAG_FALLBACK = 2u;    // a table or a video exceeds the device vote's bounds: vote on the host
+int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_n_runs, uint32_t run_cap,
+                 const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                 uint64_t n_pairs, const nb200_match_params *params);
 
 // vote.cpp ---------------------------------------------------------------
 void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order

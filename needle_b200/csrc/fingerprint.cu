@@ -853,7 +853,7 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
                                      uint32_t stride, uint64_t delay_ns, uint64_t item_ns,
                                      const uint64_t *seek_to_ns, nb200_hashset **out,
                                      void *ext_hashes = nullptr, void *ext_ts = nullptr,
-                                     uint64_t ext_capacity = 0) {
+                                     uint64_t ext_capacity = 0, bool wait = true) {
     if (stride == 0) return NB200_ERR_INVALID_ARGUMENT;   // Rust's step_by(0) panics
     if (ps->n_segments % 2 != 0) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -928,11 +928,11 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
     }
     if (frames > 0) {
         const size_t b_seg = (size_t)nseg * sizeof(FpSegment);
-        if (ctx->d_fp_desc.reserve(b_seg) != NB200_OK || ctx->h_stage.reserve(b_seg) != NB200_OK ||
+        if (ctx->d_fp_desc.reserve(b_seg) != NB200_OK || ctx->h_fp_stage.reserve(b_seg) != NB200_OK ||
             ctx->d_chroma.reserve((size_t)(frames + 8) * FP_BANDS * sizeof(float)) != NB200_OK)
             return fail(NB200_ERR_CUDA);
-        memcpy(ctx->h_stage.p, segs.data(), b_seg);
-        NB_CUDA_F(cudaMemcpyAsync(ctx->d_fp_desc.p, ctx->h_stage.p, b_seg, cudaMemcpyHostToDevice, st));
+        memcpy(ctx->h_fp_stage.p, segs.data(), b_seg);
+        NB_CUDA_F(cudaMemcpyAsync(ctx->d_fp_desc.p, ctx->h_fp_stage.p, b_seg, cudaMemcpyHostToDevice, st));
 
         K1Args k1;
         k1.pcm = ps->d_pcm.as<int16_t>();
@@ -1030,8 +1030,9 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
             ctx->ev_valid[1] = true;
             ctx->n_launches++;
         }
-        // h_stage is reused by later calls
-        NB_CUDA_F(cudaStreamSynchronize(st));
+        // the caller's PCM (pipelined copy) and h_fp_stage are free again once the stream drains; a
+        // caller that goes on to search the season on the same stream waits once, at the very end
+        if (wait) NB_CUDA_F(cudaStreamSynchronize(st));
     }
 #undef NB_CUDA_F
     *out = hs;
@@ -1353,16 +1354,46 @@ int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64
         NB_TRY(pcmset_make(ctx, pcm, n_samples_total, channels, 2 * n_videos, false, &ps));
         NB_TRY(ensure_fp_tables(ctx));
         st = fingerprint_run_pipelined(ctx, ps, pcm, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
-                                       NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs);
+                                       NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs, nullptr, nullptr, 0,
+                                       /*wait=*/false);
     } else {
         NB_TRY(nb200_pcmset_upload(ctx, pcm, n_samples_total, channels, 2 * n_videos, &ps));
-        st = fingerprint_run_impl(ctx, ps, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
-                                  NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs);
+        st = fingerprint_run_pipelined(ctx, ps, nullptr, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
+                                       NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs, nullptr, nullptr, 0,
+                                       /*wait=*/false);
     }
-    nb200_pcmset_free(ps);
-    if (st != NB200_OK) return st;
+    if (st != NB200_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        nb200_pcmset_free(ps);
+        return st;
+    }
+    // the match and the vote queue up behind K1/K2 on the same stream; nb200_search_hashset
+    // synchronises once, after which the PCM, the season and the caller's buffers are free
     std::vector<uint64_t> hd(n_videos, hash_duration_ns);
     st = nb200_search_hashset(ctx, hs, hd.data(), params, results);
+    if (st != NB200_OK) cudaStreamSynchronize(ctx->stream);
+    nb200_pcmset_free(ps);
+    nb200_hashset_free(hs);
+    return st;
+}
+
+/* Analyzer + Comparator on PCM that is already resident in HBM: K1, K2, the match, simhash
+ * and the vote are enqueued back to back; one synchronisation at the end. */
+int nb200_pcmset_search(nb200_ctx *ctx, const nb200_pcmset *ps, const uint64_t *seek_to_ns,
+                        uint64_t hash_duration_ns, const nb200_match_params *params,
+                        nb200_search_result *results) {
+    if (!ctx || !ps || !params || !results) return NB200_ERR_NULL_ARGUMENT;
+    if (ps->n_segments < 4 || ps->n_segments % 2 != 0) return NB200_ERR_COMPARATOR_MINIMUM_PATHS;
+    const uint64_t stride = (hash_duration_ns / 1000000ull) / NB200_ITEM_DURATION_MS;
+    if (stride == 0 || stride > 0xffffffffull) return NB200_ERR_INVALID_ARGUMENT;
+    nb200_hashset *hs = nullptr;
+    NB_TRY(fingerprint_run_pipelined(ctx, ps, nullptr, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
+                                     NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs, nullptr, nullptr, 0,
+                                     /*wait=*/false));
+    std::vector<uint64_t> hd(ps->n_segments / 2, hash_duration_ns);
+    int st = nb200_search_hashset(ctx, hs, hd.data(), params, results);
+    if (st != NB200_OK) cudaStreamSynchronize(ctx->stream);
     nb200_hashset_free(hs);
     return st;
 }

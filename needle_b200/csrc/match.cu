@@ -55,7 +55,8 @@ struct MatchProblem {
     uint32_t lcand;         // >= 1
     uint32_t n_bands;       // warp tiles per row chunk
     uint32_t tile_begin;    // first global tile id
-    uint32_t pad;
+    uint32_t group;         // 2 * (global pair index) + is_ending
+    uint32_t src_seg, dst_seg;   // segment indices (2 * video + is_ending): where lcand comes from
 };
 
 struct MatchArgs {
@@ -67,10 +68,21 @@ struct MatchArgs {
     uint32_t n_tiles;
     uint32_t threshold;
     uint32_t run_cap;
-    // counters[0] = tile cursor, [1] = run count, [2] = error flags
+    // 0: run; 1: run iff every problem's lcand >= 63 (the fast kernel's precondition);
+    // 2: run iff not.  The decision is made on the device (problem_finalize_kernel), so the
+    // host never waits for the run-length bounds: it launches both kernels, one returns.
+    uint32_t mode;
+    // counters[0] = tile cursor, [1] = run count, [2] = error flags, [3] = ~(min lcand)
     unsigned int *counters;
     DeviceRun *runs;
 };
+
+constexpr uint32_t FAST_MIN_LCAND = 63;
+__device__ __forceinline__ bool not_my_turn(const MatchArgs &a) {
+    if (a.mode == 0) return false;
+    const uint32_t min_lcand = ~a.counters[3];
+    return (a.mode == 1) != (min_lcand >= FAST_MIN_LCAND);
+}
 
 __device__ __forceinline__ bool hamming_match(uint32_t a, uint32_t b, uint32_t T) {
     return (uint32_t)__popc(a ^ b) <= T;
@@ -111,6 +123,8 @@ __device__ __noinline__ void check_emit(const EmitCtx a, uint32_t problem, int i
             r.len = (uint32_t)len;
             r.src_simhash = 0;
             r.dst_simhash = 0;
+            r.group = pr.group;
+            r.reserved = 0;
             r.src_start_ns = s_start;
             r.src_end_ns = s_end;
             r.dst_start_ns = d_start;
@@ -175,6 +189,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchA
     const uint32_t T = a.threshold;
     const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
     const int ybias = -(int)(T + 1);    // popc + ybias < 0  <=>  popc <= T
+    if (not_my_turn(a)) return;
 
     for (;;) {
         uint32_t tile = 0;
@@ -406,6 +421,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
     uint32_t *dst_t = s_dst[warp];
     const int T = (int)a.threshold;
     const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
+    if (not_my_turn(a)) return;
 
     for (;;) {
         uint32_t tile = 0;
@@ -552,35 +568,53 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
 // One warp per run; lane b counts bit b.
 __global__ void __launch_bounds__(128) simhash_kernel(const uint32_t *__restrict__ hashes,
                                                       const MatchProblem *__restrict__ problems,
-                                                      DeviceRun *runs, uint32_t n_runs) {
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                      DeviceRun *runs, const unsigned int *__restrict__ counters,
+                                                      uint32_t run_cap) {
+    // the run count lives on the device: the host has not waited for the match kernel
+    const uint32_t n_runs = min(counters[1], run_cap);
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp_global >= n_runs) return;
-    DeviceRun r = runs[warp_global];
-    const MatchProblem pr = problems[r.problem];
-    const uint32_t count = r.len + 1;
-    uint32_t out[2];
+    for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_runs; w += n_warps) {
+        const DeviceRun r = runs[w];
+        const MatchProblem pr = problems[r.problem];
+        const uint32_t count = r.len + 1;
+        uint32_t out[2];
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const uint32_t *h = hashes + (side == 0 ? pr.src_off + (r.i_end - r.len)
-                                                : pr.dst_off + (r.j_end - r.len));
-        uint32_t ones = 0;
-        for (uint32_t base = 0; base < count; base += 32) {
-            uint32_t mine = (base + lane < count) ? h[base + lane] : 0u;
-            const uint32_t lim = min(32u, count - base);
-            for (uint32_t k = 0; k < lim; k++) {
-                uint32_t v = __shfl_sync(0xffffffffu, mine, (int)k);
-                ones += (v >> lane) & 1u;
+        for (int side = 0; side < 2; side++) {
+            const uint32_t *h = hashes + (side == 0 ? pr.src_off + (r.i_end - r.len)
+                                                    : pr.dst_off + (r.j_end - r.len));
+            uint32_t ones = 0;
+            for (uint32_t base = 0; base < count; base += 32) {
+                uint32_t mine = (base + lane < count) ? h[base + lane] : 0u;
+                const uint32_t lim = min(32u, count - base);
+                for (uint32_t k = 0; k < lim; k++) {
+                    uint32_t v = __shfl_sync(0xffffffffu, mine, (int)k);
+                    ones += (v >> lane) & 1u;
+                }
             }
+            // v[b] = ones - (count - ones) > 0
+            const bool bit = 2u * ones > count;
+            out[side] = __ballot_sync(0xffffffffu, bit);
         }
-        // v[b] = ones - (count - ones) > 0
-        const bool bit = 2u * ones > count;
-        out[side] = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) {
+            runs[w].src_simhash = out[0];
+            runs[w].dst_simhash = out[1];
+        }
     }
-    if (lane == 0) {
-        runs[warp_global].src_simhash = out[0];
-        runs[warp_global].dst_simhash = out[1];
-    }
+}
+
+// lcand of every problem from the per-segment bounds (both tilings of the problem list),
+// and the smallest lcand overall, which decides between the fast and the general kernel.
+__global__ void problem_finalize_kernel(MatchProblem *__restrict__ fast, MatchProblem *__restrict__ general,
+                                        const uint32_t *__restrict__ lmin, uint32_t n_problems,
+                                        unsigned int *__restrict__ counters) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_problems) return;
+    const MatchProblem *any = fast ? fast : general;
+    const uint32_t lc = max(1u, max(lmin[any[p].src_seg], lmin[any[p].dst_seg]));
+    if (fast) fast[p].lcand = lc;
+    if (general) general[p].lcand = lc;
+    atomicMax(&counters[3], ~lc);
 }
 
 // Per segment: the smallest run length that can satisfy ts[i] - ts[i-len] >= min
@@ -620,8 +654,12 @@ __global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *_
 
 // ------------------------------------------------------------------- host
 
-int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pairs)[2],
-                   uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out) {
+// Enqueue the whole match stage on ctx->stream without waiting for anything:
+// run-length bounds, problem tables (both tilings), the fast and the general
+// kernel (the device decides which of the two does the work), simhash.  Runs
+// are left in ctx->d_runs, their count in ctx->d_counters[1].
+int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pairs)[2], uint64_t n_pairs,
+                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out) {
     nb200_hashset *hs = const_cast<nb200_hashset *>(hs_c);
     if (params->hash_match_threshold > 32) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -631,69 +669,26 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
         pairs = reinterpret_cast<const uint32_t(*)[2]>(default_flat.data());
         n_pairs = default_flat.size() / 2;
     }
+    if (2 * (n_pairs + (uint64_t)pair_base) >= 0xffffffffull) return NB200_ERR_TOO_LARGE;
     const bool endings = params->include_endings != 0;
+    const bool want_fast = !ctx->force_general_match;
     cudaStream_t s = ctx->stream;
+    out->problem_pair.clear();
+    out->problem_is_ending.clear();
 
-    // run-length lower bounds per segment, computed where the timestamps live
-    const uint32_t nseg = 2 * hs->n_videos;
-    std::vector<uint32_t> lmin(nseg, 1);
-    if (nseg > 0 && hs->dev_total > 0) {
-        PhaseTimer pt(ctx, NB200_PHASE_LMIN);
-        const size_t b_tab = (size_t)nseg * sizeof(SegTab), b_lmin = (size_t)nseg * sizeof(uint32_t);
-        if (ctx->h_stage.reserve(b_tab + b_lmin) != NB200_OK || ctx->d_segtab.reserve(b_tab) != NB200_OK ||
-            ctx->d_lmin.reserve(b_lmin) != NB200_OK)
-            return NB200_ERR_CUDA;
-        SegTab *tab = ctx->h_stage.as<SegTab>();
-        uint32_t *init = reinterpret_cast<uint32_t *>(tab + nseg);
-        for (uint32_t k = 0; k < nseg; k++) {
-            tab[k] = {hs->dev_offset[k], hs->seg_len[k]};
-            const uint64_t mn = (k & 1) ? params->min_ending_ns : params->min_opening_ns;
-            // n < 2 or min == 0: every run is a candidate; else start from "no window qualifies"
-            init[k] = (hs->seg_len[k] < 2 || mn == 0) ? 1u : std::min<uint32_t>(hs->seg_len[k], 0x7fffffffu);
-        }
-        NB_CUDA(cudaMemcpyAsync(ctx->d_segtab.p, tab, b_tab, cudaMemcpyHostToDevice, s));
-        NB_CUDA(cudaMemcpyAsync(ctx->d_lmin.p, init, b_lmin, cudaMemcpyHostToDevice, s));
-        uint32_t max_len = 1;
-        for (uint32_t k = 0; k < nseg; k++) max_len = std::max(max_len, hs->seg_len[k]);
-        seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
-            hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), params->min_opening_ns, params->min_ending_ns,
-            ctx->d_lmin.as<uint32_t>());
-        NB_CUDA(cudaGetLastError());
-        ctx->n_launches++;
-        NB_CUDA(cudaMemcpyAsync(init, ctx->d_lmin.p, b_lmin, cudaMemcpyDeviceToHost, s));
-        NB_CUDA(cudaStreamSynchronize(s));
-        for (uint32_t k = 0; k < nseg; k++) lmin[k] = std::max(1u, init[k]);
-    }
-
-    // the fast kernel needs every qualifying run to span a full aligned 32-row word
-    uint32_t min_lcand = 0xffffffffu;
+    PhaseTimer phase_setup(ctx, NB200_PHASE_MATCH_SETUP);
+    // problems, tiled for the fast kernel (wrapped diagonals) and for the general one
+    std::vector<MatchProblem> prob_f, prob_g;
+    prob_f.reserve(n_pairs * (endings ? 2 : 1));
+    prob_g.reserve(n_pairs * (endings ? 2 : 1));
+    uint64_t tiles_f = 0, tiles_g = 0, cells = 0;
     for (uint64_t k = 0; k < n_pairs; k++) {
         const uint32_t a = pairs[k][0], b = pairs[k][1];
         if (a >= hs->n_videos || b >= hs->n_videos) return NB200_ERR_INVALID_ARGUMENT;
-        for (int e = 0; e < (endings ? 2 : 1); e++)
-            if (hs->seg_len[2 * a + e] >= 2 && hs->seg_len[2 * b + e] >= 2)
-                min_lcand = std::min(min_lcand, std::max(1u, std::max(lmin[2 * a + e], lmin[2 * b + e])));
-    }
-    const bool fast = min_lcand >= 63 && !ctx->force_general_match;
-
-    std::unique_ptr<PhaseTimer> phase(new PhaseTimer(ctx, NB200_PHASE_MATCH_SETUP));
-    auto rs = new nb200_runset();
-    std::vector<MatchProblem> problems;
-    problems.reserve(n_pairs * (endings ? 2 : 1));
-    uint64_t tiles = 0, cells = 0;
-    for (uint64_t k = 0; k < n_pairs; k++) {
-        const uint32_t a = pairs[k][0], b = pairs[k][1];
-        if (a >= hs->n_videos || b >= hs->n_videos) {
-            delete rs;
-            return NB200_ERR_INVALID_ARGUMENT;
-        }
         for (int e = 0; e < (endings ? 2 : 1); e++) {
             const uint32_t sa = 2 * a + e, sb = 2 * b + e;
             const uint32_t n = hs->seg_len[sa], m = hs->seg_len[sb];
-            if (e == 1 && (n == 0 || m == 0)) {   // comparator.rs:271-273
-                delete rs;
-                return NB200_ERR_NO_ENDING;
-            }
+            if (e == 1 && (n == 0 || m == 0)) return NB200_ERR_NO_ENDING;   // comparator.rs:271-273
             cells += (uint64_t)n * m;
             if (n < 2 || m < 2) continue;   // rows/cols 0 never match: no run possible (:165-167,179)
             MatchProblem pr;
@@ -702,132 +697,206 @@ int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*p
             pr.dst_off = hs->dev_offset[sb];
             pr.m = m;
             pr.min_ns = e ? params->min_ending_ns : params->min_opening_ns;
-            pr.lcand = std::max(1u, std::max(lmin[sa], lmin[sb]));
+            pr.lcand = 1;   // problem_finalize_kernel
+            pr.group = (uint32_t)(2 * (k + pair_base) + (uint64_t)e);
+            pr.src_seg = sa;
+            pr.dst_seg = sb;
             const uint64_t chunks = (n + MATCH_R - 1) / MATCH_R;
+            pr.n_bands = (uint32_t)(((uint64_t)m - 1 + MATCH_DW - 1) / MATCH_DW);
+            pr.tile_begin = (uint32_t)tiles_f;
+            tiles_f += chunks * pr.n_bands;
+            prob_f.push_back(pr);
             // diagonals per chunk: (m-1) + (R-1) + up to 3 of alignment slack
-            pr.n_bands = fast ? (uint32_t)(((uint64_t)m - 1 + MATCH_DW - 1) / MATCH_DW)
-                              : (uint32_t)(((uint64_t)m + MATCH_R + 1 + MATCH_DW - 1) / MATCH_DW);
-            pr.tile_begin = (uint32_t)tiles;
-            pr.pad = 0;
-            tiles += chunks * pr.n_bands;
-            if (tiles >= 0xfffffff0ull) {
-                delete rs;
-                return NB200_ERR_TOO_LARGE;
-            }
-            problems.push_back(pr);
-            rs->problem_pair.push_back((uint32_t)k);
-            rs->problem_is_ending.push_back((uint8_t)e);
+            pr.n_bands = (uint32_t)(((uint64_t)m + MATCH_R + 1 + MATCH_DW - 1) / MATCH_DW);
+            pr.tile_begin = (uint32_t)tiles_g;
+            tiles_g += chunks * pr.n_bands;
+            prob_g.push_back(pr);
+            if (tiles_g >= 0xfffffff0ull) return NB200_ERR_TOO_LARGE;
+            out->problem_pair.push_back((uint32_t)k);
+            out->problem_is_ending.push_back((uint8_t)e);
         }
     }
-    rs->n_cells = cells;
-    const uint32_t n_problems = (uint32_t)problems.size();
-    const uint32_t n_tiles = (uint32_t)tiles;
-    if (n_problems == 0) {
-        *out = rs;
-        return NB200_OK;
-    }
-
-    std::vector<uint32_t> tile_end(n_problems);
-    for (uint32_t p = 0; p < n_problems; p++)
-        tile_end[p] = (p + 1 < n_problems) ? problems[p + 1].tile_begin : n_tiles;
-    const uint32_t n_lut = (n_tiles >> LUT_SHIFT) + 1;
-    std::vector<uint32_t> lut(n_lut);
-    {
-        uint32_t p = 0;
-        for (uint32_t k = 0; k < n_lut; k++) {
-            const uint32_t t = k << LUT_SHIFT;
-            while (p + 1 < n_problems && tile_end[p] <= t) p++;
-            lut[k] = p;
-        }
-    }
-
-    // upload descriptors through pinned staging
-    const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem);
-    const size_t b_tend = (size_t)n_problems * sizeof(uint32_t);
-    const size_t b_lut = (size_t)n_lut * sizeof(uint32_t);
-    auto fail = [&](int st) {
-        delete rs;
-        return st;
-    };
-    if (ctx->h_stage.reserve(b_prob + b_tend + b_lut) != NB200_OK) return fail(NB200_ERR_CUDA);
-    if (ctx->d_problems.reserve(b_prob) != NB200_OK || ctx->d_tile_end.reserve(b_tend) != NB200_OK ||
-        ctx->d_lut.reserve(b_lut) != NB200_OK || ctx->d_counters.reserve(64) != NB200_OK)
-        return fail(NB200_ERR_CUDA);
-    char *st = ctx->h_stage.as<char>();
-    memcpy(st, problems.data(), b_prob);
-    memcpy(st + b_prob, tile_end.data(), b_tend);
-    memcpy(st + b_prob + b_tend, lut.data(), b_lut);
-#define NB_CUDA_F(expr)                          \
-    do {                                         \
-        cudaError_t _e = (expr);                 \
-        if (_e != cudaSuccess) {                 \
-            set_last_error(#expr, _e);           \
-            return fail(NB200_ERR_CUDA);         \
-        }                                        \
-    } while (0)
-    NB_CUDA_F(cudaMemcpyAsync(ctx->d_problems.p, st, b_prob, cudaMemcpyHostToDevice, s));
-    NB_CUDA_F(cudaMemcpyAsync(ctx->d_tile_end.p, st + b_prob, b_tend, cudaMemcpyHostToDevice, s));
-    NB_CUDA_F(cudaMemcpyAsync(ctx->d_lut.p, st + b_prob + b_tend, b_lut, cudaMemcpyHostToDevice, s));
-
+    out->n_cells = cells;
+    const uint32_t n_problems = (uint32_t)prob_f.size();
+    out->n_problems = n_problems;
     uint32_t run_cap = std::max<uint32_t>(4096u, (uint32_t)std::min<uint64_t>(n_problems * 8ull, 1u << 22));
+    run_cap = std::max(run_cap, run_cap_min);
     if (ctx->d_runs.bytes / sizeof(DeviceRun) > run_cap)
         run_cap = (uint32_t)std::min<uint64_t>(ctx->d_runs.bytes / sizeof(DeviceRun), 0xffffffffull);
-    unsigned int h_counters[4];
-    phase.reset(new PhaseTimer(ctx, NB200_PHASE_MATCH));
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if (ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK) return fail(NB200_ERR_CUDA);
-        NB_CUDA_F(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
-        MatchArgs args;
-        args.hashes = hs->d_hashes.as<uint32_t>();
-        args.ts = hs->d_ts.as<uint64_t>();
+    out->run_cap = run_cap;
+    if (ctx->d_counters.reserve(64) != NB200_OK || ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK)
+        return NB200_ERR_CUDA;
+    NB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
+    ctx->ev_valid[2] = ctx->ev_valid[3] = false;
+    if (n_problems == 0) return NB200_OK;
+
+    auto tile_tables = [](const std::vector<MatchProblem> &pb, uint32_t n_tiles, std::vector<uint32_t> &tile_end,
+                          std::vector<uint32_t> &lut) {
+        const uint32_t np = (uint32_t)pb.size();
+        tile_end.resize(np);
+        for (uint32_t p = 0; p < np; p++) tile_end[p] = (p + 1 < np) ? pb[p + 1].tile_begin : n_tiles;
+        lut.resize((n_tiles >> LUT_SHIFT) + 1);
+        uint32_t p = 0;
+        for (uint32_t k = 0; k < lut.size(); k++) {
+            const uint32_t t = k << LUT_SHIFT;
+            while (p + 1 < np && tile_end[p] <= t) p++;
+            lut[k] = p;
+        }
+    };
+    std::vector<uint32_t> tend_f, lut_f, tend_g, lut_g;
+    if (want_fast) tile_tables(prob_f, (uint32_t)tiles_f, tend_f, lut_f);
+    tile_tables(prob_g, (uint32_t)tiles_g, tend_g, lut_g);
+
+    // one pinned staging area for everything this call uploads; it is rewritten by the next
+    // match only, and every public entry point synchronises before it returns
+    const uint32_t nseg = 2 * hs->n_videos;
+    const size_t b_tab = (size_t)nseg * sizeof(SegTab), b_lmin = (size_t)nseg * sizeof(uint32_t);
+    const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem), b_tend = (size_t)n_problems * sizeof(uint32_t);
+    const size_t b_lut_f = lut_f.size() * sizeof(uint32_t), b_lut_g = lut_g.size() * sizeof(uint32_t);
+    const size_t total = b_tab + b_lmin + 2 * (b_prob + b_tend) + b_lut_f + b_lut_g;
+    if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_segtab.reserve(b_tab) != NB200_OK ||
+        ctx->d_lmin.reserve(b_lmin) != NB200_OK || ctx->d_problems.reserve(b_prob) != NB200_OK ||
+        ctx->d_tile_end.reserve(b_tend) != NB200_OK || ctx->d_lut.reserve(std::max<size_t>(b_lut_f, 4)) != NB200_OK ||
+        ctx->d_problems_g.reserve(b_prob) != NB200_OK || ctx->d_tile_end_g.reserve(b_tend) != NB200_OK ||
+        ctx->d_lut_g.reserve(b_lut_g) != NB200_OK)
+        return NB200_ERR_CUDA;
+    char *st = ctx->h_stage.as<char>();
+    size_t pos = 0;
+    auto put = [&](void *dev, const void *src, size_t bytes) -> cudaError_t {
+        if (bytes == 0) return cudaSuccess;
+        memcpy(st + pos, src, bytes);
+        cudaError_t e = cudaMemcpyAsync(dev, st + pos, bytes, cudaMemcpyHostToDevice, s);
+        pos += bytes;
+        return e;
+    };
+
+    // run-length lower bounds per segment, computed where the timestamps live
+    uint32_t max_len = 1;
+    {
+        std::vector<SegTab> tab(nseg);
+        std::vector<uint32_t> init(nseg);
+        for (uint32_t k = 0; k < nseg; k++) {
+            tab[k] = {hs->dev_offset[k], hs->seg_len[k]};
+            const uint64_t mn = (k & 1) ? params->min_ending_ns : params->min_opening_ns;
+            // n < 2 or min == 0: every run is a candidate; else start from "no window qualifies"
+            init[k] = (hs->seg_len[k] < 2 || mn == 0) ? 1u : std::min<uint32_t>(hs->seg_len[k], 0x7fffffffu);
+            max_len = std::max(max_len, hs->seg_len[k]);
+        }
+        NB_CUDA(put(ctx->d_segtab.p, tab.data(), b_tab));
+        NB_CUDA(put(ctx->d_lmin.p, init.data(), b_lmin));
+    }
+    seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
+        hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), params->min_opening_ns, params->min_ending_ns,
+        ctx->d_lmin.as<uint32_t>());
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    if (want_fast) {
+        NB_CUDA(put(ctx->d_problems.p, prob_f.data(), b_prob));
+        NB_CUDA(put(ctx->d_tile_end.p, tend_f.data(), b_tend));
+        NB_CUDA(put(ctx->d_lut.p, lut_f.data(), b_lut_f));
+    }
+    NB_CUDA(put(ctx->d_problems_g.p, prob_g.data(), b_prob));
+    NB_CUDA(put(ctx->d_tile_end_g.p, tend_g.data(), b_tend));
+    NB_CUDA(put(ctx->d_lut_g.p, lut_g.data(), b_lut_g));
+    problem_finalize_kernel<<<(n_problems + 255) / 256, 256, 0, s>>>(
+        want_fast ? ctx->d_problems.as<MatchProblem>() : nullptr, ctx->d_problems_g.as<MatchProblem>(),
+        ctx->d_lmin.as<uint32_t>(), n_problems, ctx->d_counters.as<unsigned int>());
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+
+    MatchArgs args;
+    args.hashes = hs->d_hashes.as<uint32_t>();
+    args.ts = hs->d_ts.as<uint64_t>();
+    args.threshold = params->hash_match_threshold;
+    args.run_cap = run_cap;
+    args.counters = ctx->d_counters.as<unsigned int>();
+    args.runs = ctx->d_runs.as<DeviceRun>();
+    auto grid_for = [&](uint64_t n_tiles) {
+        return std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
+    };
+    NB_CUDA(cudaEventRecord(ctx->ev[4], s));
+    if (want_fast) {
         args.problems = ctx->d_problems.as<MatchProblem>();
         args.tile_end = ctx->d_tile_end.as<uint32_t>();
         args.lut = ctx->d_lut.as<uint32_t>();
-        args.n_tiles = n_tiles;
-        args.threshold = params->hash_match_threshold;
-        args.run_cap = run_cap;
-        args.counters = ctx->d_counters.as<unsigned int>();
-        args.runs = ctx->d_runs.as<DeviceRun>();
-        const uint32_t warps_needed = n_tiles;
-        uint32_t grid = (uint32_t)ctx->sm_count * 4;
-        grid = std::min<uint32_t>(grid, (warps_needed + MATCH_WARPS - 1) / MATCH_WARPS);
-        NB_CUDA_F(cudaEventRecord(ctx->ev[4], s));
-        if (fast && ctx->match_dense)
-            match_fast_kernel<false><<<grid, MATCH_WARPS * 32, 0, s>>>(args);
-        else if (fast)
-            match_fast_kernel<true><<<grid, MATCH_WARPS * 32, 0, s>>>(args);
+        args.n_tiles = (uint32_t)tiles_f;
+        args.mode = 1;
+        if (ctx->match_dense)
+            match_fast_kernel<false><<<grid_for(tiles_f), MATCH_WARPS * 32, 0, s>>>(args);
         else
-            match_kernel<<<grid, MATCH_WARPS * 32, 0, s>>>(args);
-        NB_CUDA_F(cudaGetLastError());
-        NB_CUDA_F(cudaEventRecord(ctx->ev[5], s));
-        ctx->ev_valid[2] = true;
+            match_fast_kernel<true><<<grid_for(tiles_f), MATCH_WARPS * 32, 0, s>>>(args);
+        NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
-        NB_CUDA_F(cudaMemcpyAsync(ctx->h_small.p, ctx->d_counters.p, 16, cudaMemcpyDeviceToHost, s));
-        NB_CUDA_F(cudaStreamSynchronize(s));
-        memcpy(h_counters, ctx->h_small.p, 16);
-        if (h_counters[2] & 1u) return fail(NB200_ERR_DURATION_UNDERFLOW);
-        if (h_counters[1] <= run_cap) break;
-        if (attempt == 1) return fail(NB200_ERR_TOO_LARGE);
-        run_cap = h_counters[1];     // exact count is known now: rerun with room for all of them
     }
-    rs->n_runs = h_counters[1];
-    phase.reset(new PhaseTimer(ctx, NB200_PHASE_SIMHASH));
-    ctx->ev_valid[3] = false;
-    if (rs->n_runs > 0) {
-        const uint32_t nr = (uint32_t)rs->n_runs;
-        NB_CUDA_F(cudaEventRecord(ctx->ev[6], s));
-        simhash_kernel<<<(nr + 3) / 4, 128, 0, s>>>(hs->d_hashes.as<uint32_t>(),
-                                                   ctx->d_problems.as<MatchProblem>(),
-                                                   ctx->d_runs.as<DeviceRun>(), nr);
-        NB_CUDA_F(cudaGetLastError());
-        NB_CUDA_F(cudaEventRecord(ctx->ev[7], s));
-        ctx->ev_valid[3] = true;
-        ctx->n_launches++;
-        if (rs->d_runs.alloc((size_t)nr * sizeof(DeviceRun), ctx->pool) != NB200_OK) return fail(NB200_ERR_CUDA);
-        NB_CUDA_F(cudaMemcpyAsync(rs->d_runs.p, ctx->d_runs.p, (size_t)nr * sizeof(DeviceRun),
-                                  cudaMemcpyDeviceToDevice, s));
+    args.problems = ctx->d_problems_g.as<MatchProblem>();
+    args.tile_end = ctx->d_tile_end_g.as<uint32_t>();
+    args.lut = ctx->d_lut_g.as<uint32_t>();
+    args.n_tiles = (uint32_t)tiles_g;
+    args.mode = want_fast ? 2 : 0;
+    match_kernel<<<grid_for(tiles_g), MATCH_WARPS * 32, 0, s>>>(args);
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    NB_CUDA(cudaEventRecord(ctx->ev[5], s));
+    ctx->ev_valid[2] = true;
+
+    NB_CUDA(cudaEventRecord(ctx->ev[6], s));
+    simhash_kernel<<<(uint32_t)ctx->sm_count * 2, 128, 0, s>>>(hs->d_hashes.as<uint32_t>(),
+                                                             ctx->d_problems_g.as<MatchProblem>(),
+                                                             ctx->d_runs.as<DeviceRun>(),
+                                                             ctx->d_counters.as<unsigned int>(), run_cap);
+    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaEventRecord(ctx->ev[7], s));
+    ctx->ev_valid[3] = true;
+    ctx->n_launches++;
+    return NB200_OK;
+}
+
+// Reads the match counters back (one synchronisation).  NB200_OK with *n_runs <= run_cap
+// when every run was stored; *n_runs > run_cap tells the caller to enqueue again with room.
+int match_collect(nb200_ctx *ctx, const MatchPending &mp, uint64_t *n_runs) {
+    cudaStream_t s = ctx->stream;
+    NB_CUDA(cudaMemcpyAsync(ctx->h_small.p, ctx->d_counters.p, 16, cudaMemcpyDeviceToHost, s));
+    NB_CUDA(cudaStreamSynchronize(s));
+    unsigned int h_counters[4];
+    memcpy(h_counters, ctx->h_small.p, 16);
+    if (h_counters[2] & 1u) return NB200_ERR_DURATION_UNDERFLOW;
+    *n_runs = h_counters[1];
+    (void)mp;
+    return NB200_OK;
+}
+
+int match_run_impl(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2],
+                   uint64_t n_pairs, const nb200_match_params *params, nb200_runset **out) {
+    MatchPending mp;
+    uint64_t n_runs = 0;
+    uint32_t cap_min = 0;
+    for (int attempt = 0;; attempt++) {
+        NB_TRY(match_enqueue(ctx, hs, pairs, n_pairs, params, 0, cap_min, &mp));
+        PhaseTimer pt(ctx, NB200_PHASE_MATCH);
+        NB_TRY(match_collect(ctx, mp, &n_runs));
+        if (n_runs <= mp.run_cap) break;
+        if (attempt == 1 || n_runs > 0xffffffffull) return NB200_ERR_TOO_LARGE;
+        cap_min = (uint32_t)n_runs;   // exact count is known now: rerun with room for all of them
     }
-#undef NB_CUDA_F
+    auto rs = new nb200_runset();
+    rs->n_cells = mp.n_cells;
+    rs->n_runs = n_runs;
+    rs->problem_pair = std::move(mp.problem_pair);
+    rs->problem_is_ending = std::move(mp.problem_is_ending);
+    if (n_runs > 0) {
+        PhaseTimer pt(ctx, NB200_PHASE_SIMHASH);
+        if (rs->d_runs.alloc((size_t)n_runs * sizeof(DeviceRun), ctx->pool) != NB200_OK) {
+            delete rs;
+            return NB200_ERR_CUDA;
+        }
+        cudaError_t e = cudaMemcpyAsync(rs->d_runs.p, ctx->d_runs.p, (size_t)n_runs * sizeof(DeviceRun),
+                                        cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMemcpyAsync(runs)", e);
+            delete rs;
+            return NB200_ERR_CUDA;
+        }
+    }
     *out = rs;
     return NB200_OK;
 }

@@ -161,7 +161,11 @@ class GpuBackend:
         return self.engine.PcmSet.upload(self.ctx, segments)
 
     def fingerprint_search(self, pcmset, plan: SeasonPlan, seek_to_ns, hash_duration_ns, params):
-        """Single-GPU path: nb200_fingerprint_run + nb200_search_hashset."""
+        """Single-GPU path: nb200_pcmset_search (K1, K2, match, simhash and the vote enqueued back
+        to back, one host wait); two calls when the videos' hash durations differ."""
+        hd = np.asarray(hash_duration_ns, dtype=np.uint64)
+        if hd.size and np.all(hd == hd[0]) and int(hd[0]) // 1_000_000 // 123 == plan.stride:
+            return pcmset.search(seek_to_ns, int(hd[0]), params)
         hs = pcmset.fingerprint(stride=plan.stride, seek_to_ns=seek_to_ns)
         try:
             return hs.search(hash_duration_ns, params)

@@ -67,6 +67,8 @@ class Context:
         check(lib().nb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None),
               "nb200_ctx_set_stream")
 
+    OPT_FORCE_GENERAL_MATCH, OPT_K1_VARIANT, OPT_MATCH_DENSE, OPT_HOST_VOTE = 1, 2, 3, 4
+
     def set_option(self, option: int, value: int):
         check(lib().nb200_ctx_set_option(self._h, option, value), "nb200_ctx_set_option")
 
@@ -85,8 +87,10 @@ class Context:
         ms = (C.c_float * 4)()
         n = C.c_uint64(0)
         check(lib().nb200_ctx_last_kernel_ms(self._h, ms, C.byref(n)), "nb200_ctx_last_kernel_ms")
+        vote = C.c_float(0)
+        check(lib().nb200_ctx_last_vote_ms(self._h, C.byref(vote)), "nb200_ctx_last_vote_ms")
         return {"fp_fft_chroma": ms[0], "fp_classify": ms[1], "match": ms[2], "simhash": ms[3],
-                "n_launches": n.value}
+                "vote": vote.value, "n_launches": n.value}
 
     # ---------------------------------------------------------- host-buffer calls
 
@@ -377,6 +381,15 @@ class PcmSet:
         check(lib().nb200_fingerprint_run(self.ctx.handle, self._h, stride, delay_ns, item_ns, ptr(seek),
                                           C.byref(out)), "nb200_fingerprint_run")
         return HashSet(self.ctx, out)
+
+    def search(self, seek_to_ns, hash_duration_ns: int, params: MatchParams):
+        """nb200_pcmset_search: fingerprint + match + vote on the resident PCM, one host wait."""
+        seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        n_videos = self.n_segments // 2
+        res = (SearchResultC * max(n_videos, 1))()
+        check(lib().nb200_pcmset_search(self.ctx.handle, self._h, ptr(seek), hash_duration_ns, C.byref(params), res),
+              "nb200_pcmset_search")
+        return _results_list(res, n_videos)
 
     def fingerprint_into(self, d_hashes: int, d_ts_ns: int, capacity: int, stride: int = 2,
                          delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS, seek_to_ns=None):

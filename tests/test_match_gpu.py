@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, OPT_MATCH_DENSE, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
+from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, OPT_MATCH_DENSE, OPT_HOST_VOTE, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -44,7 +44,12 @@ def check_season(ctx, orc, season, vote=True, **kw):
     assert np.array_equal(rs.download(), runs)
     if vote:
         assert ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, p) == want_results
-        assert hs.search(season.hash_duration_ns, p) == want_results
+        assert hs.search(season.hash_duration_ns, p) == want_results       # device vote (vote_device.cu)
+        ctx.set_option(OPT_HOST_VOTE, 1)
+        try:
+            assert hs.search(season.hash_duration_ns, p) == want_results   # runs downloaded, host vote (vote.cpp)
+        finally:
+            ctx.set_option(OPT_HOST_VOTE, 0)
         # host-only vote on the downloaded runs
         assert engine.vote(season.hash_duration_ns, p, runs) == want_results
     return runs, want_results
