@@ -224,6 +224,10 @@ def run_reference(args):
 # ------------------------------------------------------------------ b200 arm
 
 def run_b200(args):
+    # a stuck collective must not hold the GPU box until the driver's limit: dump every thread's
+    # stack and leave
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("NB200_BENCH_WATCHDOG_S", "420")), exit=True)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"    # NCCL's version banner goes to stdout; this run prints one JSON line
     import torch
@@ -301,9 +305,10 @@ def run_b200(args):
     else:
         d2h_bytes = 64 * n_runs_local + 16     # this rank's runs (they carry their timestamps) + counters
 
-    # bring the clocks up before anything is timed (idle parts sit at 120 MHz)
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < float(os.environ.get("NB200_BENCH_SPIN_S", "1.5")):
+    # bring the clocks up before anything is timed (idle parts sit at 120 MHz).  A FIXED number of
+    # steps: every step holds collectives, so all ranks must run the same count (a per-rank
+    # time limit would let one rank do one step more than another and misalign them)
+    for _ in range(int(os.environ.get("NB200_BENCH_SPIN_STEPS", "500"))):
         job.run_resident(pcmset)
 
     sampler = ClockSampler(local_rank)

@@ -94,7 +94,13 @@ enum {
      * per-video results; 1 downloads the runs and votes on the host (vote.cpp) instead.
      * Results are identical; the host vote is also the automatic fallback when a table
      * has more runs, or a video more candidates, than the device kernels are sized for. */
-    NB200_OPT_HOST_VOTE = 4
+    NB200_OPT_HOST_VOTE = 4,
+    /* NB200_OPT_DEFER_WAIT (0|1): nb200_fingerprint_run_into / nb200_fingerprint_host_into return
+     * as soon as their work is enqueued on the context's stream instead of waiting for it.  For
+     * pipelines that go on to exchange and match on the same stream (the multi-GPU job) and
+     * synchronise once at the end; host PCM passed to nb200_fingerprint_host_into must then stay
+     * untouched until that synchronisation. */
+    NB200_OPT_DEFER_WAIT = 5
 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 
@@ -347,6 +353,28 @@ int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64
 int nb200_pcmset_search(nb200_ctx *ctx, const nb200_pcmset *ps, const uint64_t *seek_to_ns,
                         uint64_t hash_duration_ns, const nb200_match_params *params,
                         nb200_search_result *results);
+
+/* ------------------------------------------- multi-GPU: run blocks in HBM
+ *
+ * A rank's share of the pair loop as ONE fixed-size device message that can be
+ * handed to a collective as it is: 64-byte header {u32 n_found, u32 n_stored,
+ * u32 flags, ...} followed by 64-byte run records (the device form of
+ * nb200_run, carrying the GLOBAL pair index pair_base + k and all four
+ * timestamps).  Nothing is waited for: the match kernels emit straight into
+ * the block on the context's stream.  block_bytes = 64 * (1 + capacity). */
+int nb200_match_export(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2], uint64_t n_pairs,
+                       const nb200_match_params *params, uint32_t pair_base, void *d_block, uint64_t block_bytes);
+/* The blocks of all ranks, back to back in device memory (an all-gather receive
+ * buffer): with do_vote != 0 the heaps are replayed and find_best_match runs on
+ * the device over all of them (pairs / n_pairs = the GLOBAL pair list, NULL = all
+ * i < j) and results[n_videos] is filled; with do_vote == 0 only the headers are
+ * checked.  Synchronises the stream once.  *max_found = the largest n_found of any
+ * block; NB200_ERR_TOO_LARGE when a block could not hold its runs (every rank sees
+ * the same headers, so every rank can repeat the step with larger blocks). */
+int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
+                      const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                      uint64_t n_pairs, const nb200_match_params *params, int do_vote,
+                      nb200_search_result *results, uint64_t *max_found);
 
 /* ------------------------------------------------------------ persistence */
 

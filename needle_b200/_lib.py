@@ -28,6 +28,7 @@ OPT_FORCE_GENERAL_MATCH = 1
 OPT_K1_VARIANT = 2
 OPT_MATCH_DENSE = 3
 OPT_HOST_VOTE = 4
+OPT_DEFER_WAIT = 5
 
 
 class Nb200Error(RuntimeError):
@@ -137,6 +138,9 @@ PROTOTYPES = {
     "nb200_analyze_search": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, _P, C.c_uint64,
                                        C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
     "nb200_pcmset_search": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), C.POINTER(SearchResultC)]),
+    "nb200_match_export": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), C.c_uint32, _P, C.c_uint64]),
+    "nb200_vote_blocks": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P, C.c_uint32, _P, C.c_uint64,
+                                    C.POINTER(MatchParams), C.c_int, C.POINTER(SearchResultC), _U64P]),
     "nb200_framehashes_write": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, _P, _P, C.c_uint64,
                                           C.c_uint64, C.c_char_p]),
     "nb200_framehashes_read": (C.c_int, [C.c_char_p, _PP, _PP, _U64P, _PP, _PP, _U64P, _U64P,

@@ -193,6 +193,9 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
     case NB200_OPT_MATCH_DENSE:
         ctx->match_dense = value != 0;
         return NB200_OK;
+    case NB200_OPT_DEFER_WAIT:
+        ctx->defer_wait = value != 0;
+        return NB200_OK;
     case NB200_OPT_HOST_VOTE:
         ctx->host_vote = value != 0;
         return NB200_OK;

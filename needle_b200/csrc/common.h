@@ -163,6 +163,7 @@ struct nb200_ctx {
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();
     // scratch reused across calls
+    bool defer_wait = false;            // *_into fingerprint calls return without waiting for the stream
     bool host_vote = false;             // searches download the runs and vote on the host (vote.cpp) instead of on the device
     nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
     nb200::DevBuf d_problems_g, d_tile_end_g, d_lut_g;   // the general kernel's tiling of the same problems
@@ -249,7 +250,8 @@ struct MatchPending {
     std::vector<uint8_t> problem_is_ending;
 };
 int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2], uint64_t n_pairs,
-                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out);
+                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out,
+                  DeviceRun *ext_runs = nullptr, uint32_t ext_cap = 0);
 // Waits for the stream and reads the counters: DURATION_UNDERFLOW, or OK with the number of
 // runs found (> run_cap: enqueue again with run_cap_min = that number).
 int match_collect(nb200_ctx *ctx, const MatchPending &mp, uint64_t *n_runs);

@@ -1154,7 +1154,7 @@ int nb200_fingerprint_run_into(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t 
     if (!ctx || !ps || !d_hashes_out || !d_ts_ns_out) return NB200_ERR_NULL_ARGUMENT;
     nb200_hashset *hs = nullptr;
     NB_TRY(fingerprint_run_pipelined(ctx, ps, nullptr, stride, delay_ns, item_ns, seek_to_ns, &hs,
-                                     d_hashes_out, d_ts_ns_out, capacity));
+                                     d_hashes_out, d_ts_ns_out, capacity, !ctx->defer_wait));
     nb200_hashset_free(hs);   // borrowed arrays: nothing is released
     return NB200_OK;
 }
@@ -1197,9 +1197,11 @@ int nb200_fingerprint_host_into(nb200_ctx *ctx, const int16_t *const *pcm, const
     nb200_hashset *hs = nullptr;
     if (st == NB200_OK)
         st = fingerprint_run_pipelined(ctx, ps, pcm, stride, delay_ns, item_ns, seek_to_ns, &hs, d_hashes_out,
-                                       d_ts_ns_out, capacity);
+                                       d_ts_ns_out, capacity, !ctx->defer_wait);
     nb200_hashset_free(hs);
-    nb200_pcmset_free(ps);   // kernels have completed (fingerprint_run_pipelined synchronises)
+    // the PCM block goes back to the context's pool; whoever takes it next is ordered behind
+    // these kernels (same stream, and the copy stream waits for the compute stream first)
+    nb200_pcmset_free(ps);
     return st;
 }
 

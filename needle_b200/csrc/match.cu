@@ -659,7 +659,8 @@ __global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *_
 // kernel (the device decides which of the two does the work), simhash.  Runs
 // are left in ctx->d_runs, their count in ctx->d_counters[1].
 int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pairs)[2], uint64_t n_pairs,
-                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out) {
+                  const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out,
+                  DeviceRun *ext_runs, uint32_t ext_cap) {
     nb200_hashset *hs = const_cast<nb200_hashset *>(hs_c);
     if (params->hash_match_threshold > 32) return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
@@ -721,11 +722,16 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     out->n_problems = n_problems;
     uint32_t run_cap = std::max<uint32_t>(4096u, (uint32_t)std::min<uint64_t>(n_problems * 8ull, 1u << 22));
     run_cap = std::max(run_cap, run_cap_min);
-    if (ctx->d_runs.bytes / sizeof(DeviceRun) > run_cap)
-        run_cap = (uint32_t)std::min<uint64_t>(ctx->d_runs.bytes / sizeof(DeviceRun), 0xffffffffull);
+    if (ext_runs) {
+        run_cap = ext_cap;   // the caller's block (an exchange send buffer): runs are emitted straight into it
+    } else {
+        if (ctx->d_runs.bytes / sizeof(DeviceRun) > run_cap)
+            run_cap = (uint32_t)std::min<uint64_t>(ctx->d_runs.bytes / sizeof(DeviceRun), 0xffffffffull);
+        if (ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK) return NB200_ERR_CUDA;
+    }
+    DeviceRun *const runs_out = ext_runs ? ext_runs : ctx->d_runs.as<DeviceRun>();
     out->run_cap = run_cap;
-    if (ctx->d_counters.reserve(64) != NB200_OK || ctx->d_runs.reserve((size_t)run_cap * sizeof(DeviceRun)) != NB200_OK)
-        return NB200_ERR_CUDA;
+    if (ctx->d_counters.reserve(64) != NB200_OK) return NB200_ERR_CUDA;
     NB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
     ctx->ev_valid[2] = ctx->ev_valid[3] = false;
     if (n_problems == 0) return NB200_OK;
@@ -810,7 +816,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     args.threshold = params->hash_match_threshold;
     args.run_cap = run_cap;
     args.counters = ctx->d_counters.as<unsigned int>();
-    args.runs = ctx->d_runs.as<DeviceRun>();
+    args.runs = runs_out;
     auto grid_for = [&](uint64_t n_tiles) {
         return std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
     };
@@ -841,8 +847,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
 
     NB_CUDA(cudaEventRecord(ctx->ev[6], s));
     simhash_kernel<<<(uint32_t)ctx->sm_count * 2, 128, 0, s>>>(hs->d_hashes.as<uint32_t>(),
-                                                             ctx->d_problems_g.as<MatchProblem>(),
-                                                             ctx->d_runs.as<DeviceRun>(),
+                                                             ctx->d_problems_g.as<MatchProblem>(), runs_out,
                                                              ctx->d_counters.as<unsigned int>(), run_cap);
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaEventRecord(ctx->ev[7], s));

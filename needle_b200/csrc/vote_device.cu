@@ -23,6 +23,7 @@
 // round-to-nearest intrinsics so that no FMA contraction can differ from Rust's f32.
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -357,4 +358,139 @@ int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_
     return NB200_OK;
 }
 
+// ------------------------------------------------------------------ run blocks
+// A rank's match output as one fixed-size message: 64-byte header, then DeviceRun records.
+// The match kernel emits straight into the records; this kernel fills in the header from
+// the match counters once the kernels before it on the stream are done.
+struct RunBlockHeader {
+    uint32_t n_found;    // runs the match found
+    uint32_t n_stored;   // min(n_found, capacity): the records that follow
+    uint32_t flags;      // bit 0: a Duration subtraction would have underflowed
+    uint32_t reserved[13];
+};
+static_assert(sizeof(RunBlockHeader) == 64, "header and records share one 64-byte grid");
+
+__global__ void block_header_kernel(RunBlockHeader *h, const unsigned int *__restrict__ counters, uint32_t cap) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint32_t n = counters[1];
+    h->n_found = n;
+    h->n_stored = min(n, cap);
+    h->flags = counters[2] & 1u;
+}
+
+// blocks of all ranks (an all-gather receive buffer) -> one contiguous run array + its length
+__global__ void block_compact_kernel(const char *__restrict__ blocks, uint32_t n_blocks, uint64_t block_bytes,
+                                     DeviceRun *__restrict__ out, unsigned int *__restrict__ total) {
+    const uint32_t b = blockIdx.y;
+    uint32_t prefix = 0, n = 0, all = 0;
+    for (uint32_t q = 0; q < n_blocks; q++) {
+        const uint32_t c = reinterpret_cast<const RunBlockHeader *>(blocks + (size_t)q * block_bytes)->n_stored;
+        if (q < b) prefix += c;
+        if (q == b) n = c;
+        all += c;
+    }
+    if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) *total = all;
+    const uint4 *src = reinterpret_cast<const uint4 *>(blocks + (size_t)b * block_bytes + sizeof(RunBlockHeader));
+    uint4 *dst = reinterpret_cast<uint4 *>(out + prefix);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < 4 * n; k += gridDim.x * blockDim.x) dst[k] = src[k];
+}
+
 }  // namespace nb200
+
+using namespace nb200;
+
+extern "C" {
+
+int nb200_match_export(nb200_ctx *ctx, const nb200_hashset *hs, const uint32_t (*pairs)[2], uint64_t n_pairs,
+                       const nb200_match_params *params, uint32_t pair_base, void *d_block, uint64_t block_bytes) {
+    if (!ctx || !hs || !params || !d_block) return NB200_ERR_NULL_ARGUMENT;
+    if (block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0) return NB200_ERR_INVALID_ARGUMENT;
+    const uint64_t cap = (block_bytes - sizeof(RunBlockHeader)) / sizeof(DeviceRun);
+    if (cap > 0x7fffffffull) return NB200_ERR_TOO_LARGE;
+    MatchPending mp;
+    // an empty slice (pairs != NULL, n_pairs == 0) still produces a valid, empty block
+    NB_TRY(match_enqueue(ctx, hs, pairs, n_pairs, params, pair_base, 0, &mp,
+                         reinterpret_cast<DeviceRun *>((char *)d_block + sizeof(RunBlockHeader)), (uint32_t)cap));
+    block_header_kernel<<<1, 32, 0, ctx->stream>>>((RunBlockHeader *)d_block, ctx->d_counters.as<unsigned int>(),
+                                                   (uint32_t)cap);
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    return NB200_OK;
+}
+
+int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes,
+                      const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                      uint64_t n_pairs, const nb200_match_params *params, int do_vote,
+                      nb200_search_result *results, uint64_t *max_found) {
+    if (!ctx || !d_blocks || !hash_duration_ns || !params || !max_found) return NB200_ERR_NULL_ARGUMENT;
+    if (do_vote && !results) return NB200_ERR_NULL_ARGUMENT;
+    if (n_blocks == 0 || block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0)
+        return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t cap = (block_bytes - sizeof(RunBlockHeader)) / sizeof(DeviceRun);
+    const uint64_t total_cap = cap * n_blocks;
+    if (total_cap >= 0x7fffffffull) return NB200_ERR_TOO_LARGE;
+    *max_found = 0;
+    ctx->ev_valid[4] = false;
+    // headers of every block for the host (overflow / underflow are decided there, by every rank alike)
+    const size_t b_hdr = (size_t)n_blocks * sizeof(RunBlockHeader);
+    NB_TRY(ctx->h_runs.reserve(b_hdr));
+    NB_CUDA(cudaMemcpy2DAsync(ctx->h_runs.p, sizeof(RunBlockHeader), d_blocks, block_bytes, sizeof(RunBlockHeader),
+                              n_blocks, cudaMemcpyDeviceToHost, s));
+    if (do_vote) {
+        NB_TRY(ctx->d_vote_gather.reserve(total_cap * sizeof(DeviceRun) + 64));
+        unsigned int *d_total = reinterpret_cast<unsigned int *>(ctx->d_vote_gather.as<char>() + total_cap * sizeof(DeviceRun));
+        block_compact_kernel<<<dim3(16, n_blocks), 256, 0, s>>>((const char *)d_blocks, n_blocks, block_bytes,
+                                                               ctx->d_vote_gather.as<DeviceRun>(), d_total);
+        NB_CUDA(cudaGetLastError());
+        ctx->n_launches++;
+        PhaseTimer pt(ctx, NB200_PHASE_VOTE);
+        NB_TRY(vote_enqueue(ctx, ctx->d_vote_gather.as<DeviceRun>(), d_total, (uint32_t)total_cap, hash_duration_ns,
+                            n_videos, pairs, n_pairs, params));
+    }
+    {
+        PhaseTimer pt(ctx, NB200_PHASE_MATCH);
+        NB_CUDA(cudaStreamSynchronize(s));
+    }
+    const RunBlockHeader *hdr = ctx->h_runs.as<RunBlockHeader>();
+    bool underflow = false, truncated = false;
+    uint64_t n_total = 0;
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        *max_found = std::max<uint64_t>(*max_found, hdr[b].n_found);
+        underflow |= (hdr[b].flags & 1u) != 0;
+        truncated |= hdr[b].n_found > hdr[b].n_stored;
+        n_total += hdr[b].n_stored;
+    }
+    if (underflow) return NB200_ERR_DURATION_UNDERFLOW;
+    if (truncated) return NB200_ERR_TOO_LARGE;   // *max_found tells the caller how big a block must be
+    if (!do_vote) return NB200_OK;
+    const size_t b_res = (size_t)n_videos * sizeof(nb200_search_result);
+    uint32_t flags[4];
+    memcpy(flags, ctx->h_results.as<char>() + b_res, sizeof(flags));
+    if (!(flags[0] & VOTE_FLAG_FALLBACK)) {
+        memcpy(results, ctx->h_results.p, b_res);
+        return (flags[0] & VOTE_FLAG_UNDERFLOW) ? NB200_ERR_DURATION_UNDERFLOW : NB200_OK;
+    }
+    // beyond the device vote's bounds: download the gathered runs, order them, vote on the host
+    std::vector<DeviceRun> raw(n_total);
+    if (n_total) {
+        NB_CUDA(cudaMemcpyAsync(raw.data(), ctx->d_vote_gather.p, n_total * sizeof(DeviceRun), cudaMemcpyDeviceToHost, s));
+        NB_CUDA(cudaStreamSynchronize(s));
+    }
+    std::sort(raw.begin(), raw.end(), [](const DeviceRun &a, const DeviceRun &b) {
+        if (a.group != b.group) return a.group < b.group;
+        if (a.i_end != b.i_end) return a.i_end > b.i_end;
+        return a.j_end > b.j_end;
+    });
+    std::vector<nb200_run> runs(std::max<size_t>(raw.size(), 1));
+    for (size_t k = 0; k < raw.size(); k++) {
+        const DeviceRun &r = raw[k];
+        runs[k] = {r.group >> 1, r.group & 1u, r.i_end, r.j_end, r.len, r.src_simhash, r.dst_simhash, 0,
+                   r.src_start_ns, r.src_end_ns, r.dst_start_ns, r.dst_end_ns};
+    }
+    PhaseTimer pt(ctx, NB200_PHASE_VOTE);
+    return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs.data(), raw.size(), nullptr, results);
+}
+
+}  // extern "C"

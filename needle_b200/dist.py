@@ -152,10 +152,17 @@ class GpuBackend:
         self.device = torch.device("cuda", device_index)
         torch.cuda.set_device(self.device)
         self.ctx = engine.Context(device_index)
-        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # One real stream for the library's kernels AND torch's collectives: torch's default
+        # stream is the NULL stream, which the library's non-blocking stream would not be ordered
+        # with.  Every method that touches torch tensors runs under `with self._on_stream()`.
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        # the *_into fingerprint calls only enqueue: the job synchronises once, after the vote
+        self.ctx.set_option(engine.Context.OPT_DEFER_WAIT, 1)
         self._run_bufs = None
-        self._cnt_bufs = None
-        self._res_bufs = None
+
+    def _on_stream(self):
+        return self.torch.cuda.stream(self.stream)
 
     def upload_pcm(self, segments):
         return self.engine.PcmSet.upload(self.ctx, segments)
@@ -174,10 +181,11 @@ class GpuBackend:
 
     def alloc_exchange(self, plan: SeasonPlan):
         t = self.torch
-        return {"hash_send": t.zeros(plan.cap, dtype=t.int32, device=self.device),
-                "ts_send": t.zeros(plan.cap, dtype=t.int64, device=self.device),
-                "hash_recv": t.zeros(plan.cap * plan.world, dtype=t.int32, device=self.device),
-                "ts_recv": t.zeros(plan.cap * plan.world, dtype=t.int64, device=self.device)}
+        with self._on_stream():
+            return {"hash_send": t.zeros(plan.cap, dtype=t.int32, device=self.device),
+                    "ts_send": t.zeros(plan.cap, dtype=t.int64, device=self.device),
+                    "hash_recv": t.zeros(plan.cap * plan.world, dtype=t.int32, device=self.device),
+                    "ts_recv": t.zeros(plan.cap * plan.world, dtype=t.int64, device=self.device)}
 
     def fingerprint_into(self, pcmset, plan: SeasonPlan, seek_to_ns, ex):
         """K1/K2 on this rank's segments, written directly into the send buffers."""
@@ -192,7 +200,8 @@ class GpuBackend:
     def exchange(self, dist, ex, plan: SeasonPlan, seek_to_ns, group=None):
         """ONE collective: the hashes.  Timestamps are a function of the index
         (analyzer.rs:309), so every rank fills in all of them itself."""
-        dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
+        with self._on_stream():
+            dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
         self.ctx.timestamps_fill(ex["ts_recv"].data_ptr(), plan.dev_offset, plan.seg_len, seek_to_ns,
                                  stride=plan.stride)
 
@@ -201,6 +210,40 @@ class GpuBackend:
         return self.engine.HashSet.view(self.ctx, h.data_ptr(), t.data_ptr(), plan.dev_offset, plan.seg_len,
                                         keepalive=(h, t))
 
+    # ---- device-resident tail: runs never visit the host ------------------------------------
+    def run_block_capacity(self, slices) -> int:
+        """Run records per rank block: the same on every rank (it sizes the collective)."""
+        cap = getattr(self, "_block_cap", 0)
+        need = max(4096, 16 * max((e - s) for s, e in slices))
+        while cap < need:
+            cap = max(4096, cap * 2)
+        self._block_cap = cap
+        return cap
+
+    def search_gathered(self, dist, season, params, my_pairs, pair_base, all_pairs, hash_duration_ns, slices,
+                        group=None):
+        """match (this rank's slice, emitted straight into its run block) -> ONE all-gather of
+        the blocks -> heap replay + find_best_match on rank 0's GPU -> 48 bytes per video come
+        back.  One host wait per job; if a block overflowed every rank sees it in the gathered
+        headers and the step is repeated with larger blocks."""
+        t = self.torch
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        while True:
+            cap = self.run_block_capacity(slices)
+            block = 64 * (1 + cap)
+            with self._on_stream():
+                if self._run_bufs is None or self._run_bufs[0].numel() != block:
+                    self._run_bufs = (t.zeros(block, dtype=t.uint8, device=self.device),
+                                      t.zeros(block * world, dtype=t.uint8, device=self.device))
+                send, recv = self._run_bufs
+                season.match_export(params, my_pairs, pair_base, send.data_ptr(), block)
+                dist.all_gather_into_tensor(recv, send, group=group)
+            results, found, truncated = self.ctx.vote_blocks(recv.data_ptr(), world, block, hash_duration_ns, params,
+                                                             pairs=all_pairs, do_vote=(rank == 0))
+            if not truncated:
+                return results
+            self._block_cap = max(self._block_cap * 2, int(found))
+
     def match(self, season, params, pairs) -> np.ndarray:
         if len(pairs) == 0:
             return np.zeros(0, dtype=RUN_DTYPE)
@@ -208,63 +251,6 @@ class GpuBackend:
         runs = rs.download()
         rs.free()
         return runs
-
-    def gather_runs(self, dist, runs, group=None):
-        """Every rank contributes its (host, sorted) run list; rank 0 gets all of them.
-        Two collectives: the counts (8 bytes per rank), then one block per rank sized by
-        the largest count (rounded up to a power of two so the buffers are reused)."""
-        t = self.torch
-        world = dist.get_world_size(group)
-        rank = dist.get_rank(group)
-        n = runs.shape[0]
-        if self._cnt_bufs is None:
-            self._cnt_bufs = (t.zeros(1, dtype=t.int64).pin_memory(), t.zeros(1, dtype=t.int64, device=self.device),
-                              t.zeros(world, dtype=t.int64, device=self.device))
-        h_cnt, d_cnt, d_cnts = self._cnt_bufs
-        h_cnt[0] = n
-        d_cnt.copy_(h_cnt, non_blocking=True)
-        dist.all_gather_into_tensor(d_cnts, d_cnt, group=group)
-        counts = d_cnts.cpu().numpy()
-        cap = 64
-        while cap < int(counts.max()):
-            cap *= 2
-        block = cap * RUN_DTYPE.itemsize
-        if self._run_bufs is None or self._run_bufs[0].numel() != block:
-            self._run_bufs = (t.zeros(block, dtype=t.uint8).pin_memory(),
-                              t.zeros(block, dtype=t.uint8, device=self.device),
-                              t.zeros(block * world, dtype=t.uint8, device=self.device),
-                              t.zeros(block * world, dtype=t.uint8).pin_memory())
-        h_send, d_send, d_recv, h_recv = self._run_bufs
-        if n:
-            h_send.numpy()[:n * RUN_DTYPE.itemsize] = np.frombuffer(runs.tobytes(), dtype=np.uint8)
-        d_send.copy_(h_send, non_blocking=True)
-        dist.all_gather_into_tensor(d_recv, d_send, group=group)
-        h_recv.copy_(d_recv, non_blocking=True)          # every rank: each votes for its share of the videos
-        t.cuda.current_stream(self.device).synchronize()
-        return unpack_run_blocks(h_recv.numpy(), counts, block)
-
-    def gather_results(self, dist, mine: np.ndarray, cap: int, group=None):
-        """Each rank's rows of the result table (cap rows, padded) -> all rows on rank 0."""
-        t = self.torch
-        world = dist.get_world_size(group)
-        nbytes = cap * RESULT_DTYPE.itemsize
-        if self._res_bufs is None or self._res_bufs[0].numel() != nbytes:
-            self._res_bufs = (t.zeros(nbytes, dtype=t.uint8).pin_memory(),
-                              t.zeros(nbytes, dtype=t.uint8, device=self.device),
-                              t.zeros(nbytes * world, dtype=t.uint8, device=self.device),
-                              t.zeros(nbytes * world, dtype=t.uint8).pin_memory())
-        h_send, d_send, d_recv, h_recv = self._res_bufs
-        h_send.numpy()[:mine.shape[0] * RESULT_DTYPE.itemsize] = np.frombuffer(mine.tobytes(), dtype=np.uint8)
-        d_send.copy_(h_send, non_blocking=True)
-        dist.all_gather_into_tensor(d_recv, d_send, group=group)
-        if dist.get_rank(group) != 0:
-            return None
-        h_recv.copy_(d_recv, non_blocking=True)
-        t.cuda.current_stream(self.device).synchronize()
-        return np.frombuffer(h_recv.numpy().tobytes(), dtype=RESULT_DTYPE).reshape(world, cap)
-
-    def vote(self, hash_duration_ns, params, runs, pairs, video_mask=None) -> np.ndarray:
-        return self.engine.vote_array(hash_duration_ns, params, runs, pairs=pairs, video_mask=video_mask)
 
     def release(self, obj):
         obj.free()
@@ -354,6 +340,13 @@ class SeasonJob:
         season = b.season_from_gathered(ex, self.plan, self.world)
         t = self._tick("exchange_enqueue", t)
         start, end = self.slices[self.rank]
+        if self.world > 1 and hasattr(b, "search_gathered"):
+            results = b.search_gathered(self.dist, season, self.params, self.pairs[start:end], start,
+                                        None if self._all_pairs else self.pairs, self.hash_duration_ns, self.slices,
+                                        self.group)
+            b.release(season)
+            self._tick("match+gather+vote", t)
+            return results
         runs = globalize_runs(b.match(season, self.params, self.pairs[start:end]), start)
         b.release(season)
         t = self._tick("match", t)

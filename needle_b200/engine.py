@@ -67,7 +67,7 @@ class Context:
         check(lib().nb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None),
               "nb200_ctx_set_stream")
 
-    OPT_FORCE_GENERAL_MATCH, OPT_K1_VARIANT, OPT_MATCH_DENSE, OPT_HOST_VOTE = 1, 2, 3, 4
+    OPT_FORCE_GENERAL_MATCH, OPT_K1_VARIANT, OPT_MATCH_DENSE, OPT_HOST_VOTE, OPT_DEFER_WAIT = 1, 2, 3, 4, 5
 
     def set_option(self, option: int, value: int):
         check(lib().nb200_ctx_set_option(self._h, option, value), "nb200_ctx_set_option")
@@ -168,6 +168,20 @@ class Context:
         sk = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
         check(lib().nb200_timestamps_fill(self._h, C.c_void_p(d_ts_ns), ptr(do), ptr(ln), ptr(sk), ln.size, stride,
                                           delay_ns, item_ns), "nb200_timestamps_fill")
+
+    def vote_blocks(self, d_blocks: int, n_blocks: int, block_bytes: int, hash_duration_ns, params: MatchParams,
+                    pairs=None, do_vote: bool = True):
+        """nb200_vote_blocks -> (results or None, max_found, truncated).  One stream synchronisation."""
+        hd = np.ascontiguousarray(hash_duration_ns, dtype=np.uint64)
+        _keep, pp, npairs = _pairs_arg(pairs)
+        res = (SearchResultC * max(hd.size, 1))()
+        found = C.c_uint64(0)
+        st = lib().nb200_vote_blocks(self._h, C.c_void_p(d_blocks), n_blocks, block_bytes, ptr(hd), hd.size, pp, npairs,
+                                     C.byref(params), 1 if do_vote else 0, res, C.byref(found))
+        if st == _lib.ERR_TOO_LARGE and found.value > (block_bytes - 64) // 64:
+            return None, found.value, True
+        check(st, "nb200_vote_blocks")
+        return (_results_list(res, hd.size) if do_vote else None), found.value, False
 
     def analyze_search(self, segments, channels, seek_to_ns, hash_duration_ns, params: MatchParams):
         """nb200_analyze_search: segments = [opening_0, ending_0, opening_1, ...] PCM arrays."""
@@ -292,6 +306,15 @@ class HashSet:
         check(lib().nb200_match_run(self.ctx.handle, self._h, pp, npairs, C.byref(params), C.byref(out)),
               "nb200_match_run")
         return RunSet(self.ctx, out)
+
+    def match_export(self, params: MatchParams, pairs, pair_base: int, d_block: int, block_bytes: int):
+        """nb200_match_export: this slice of the pair list matched straight into a run block in
+        device memory (asynchronous; pairs must be an explicit, possibly empty, list)."""
+        a = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        keep = a if a.shape[0] else np.zeros((1, 2), np.uint32)     # an empty slice still needs a non-NULL list
+        check(lib().nb200_match_export(self.ctx.handle, self._h, keep.ctypes.data_as(C.c_void_p), a.shape[0],
+                                       C.byref(params), pair_base, C.c_void_p(d_block), block_bytes),
+              "nb200_match_export")
 
     def search(self, hash_duration_ns, params: MatchParams):
         n, _, _ = self.info()
