@@ -244,6 +244,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == max(args.gpus, 1) or world == 1, "launch with torchrun --nproc-per-node = --gpus"
 
+    # N > 1: every rank streams 556 MB of pinned PCM per step; keep each rank's host memory on
+    # its GPU's NUMA node (N = 1 keeps all cores: the CPU baseline runs in this process)
+    numa_bound = nd.bind_host_to_gpu_numa(local_rank) if world > 1 else False
     per_season = args.episodes
     n_videos = per_season * world
     backend = nd.GpuBackend(local_rank)
@@ -446,7 +449,7 @@ def run_b200(args):
         },
         "e2e": {"value": n_pairs_total / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "host_numa_bound": bool(numa_bound),
                 "call": "nb200_analyze_search (C ABI, pinned host PCM)" if one_call else
                         "SeasonJob.run_host (pinned host PCM per rank)"},
         "gpu_launches": int(launches),

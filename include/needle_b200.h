@@ -388,6 +388,36 @@ int nb200_framehashes_read(const char *path, uint32_t **open_hash, uint64_t **op
                            uint64_t *n_open, uint32_t **end_hash, uint64_t **end_ts_ns,
                            uint64_t *n_end, uint64_t *hash_duration_ns, char *md5_out);
 
+/* ------------------------------------- libneedle.so (include/needle.h) hooks
+ *
+ * The needle-capi ABI of include/needle.h is served by libneedle.so (capi.cpp),
+ * which links against this library.  In the reference, FFmpeg demuxes, decodes and
+ * resamples to 11025 Hz S16 before Chromaprint sees a sample (analyzer.rs:170-283);
+ * that stays host code.  libneedle.so gets its PCM from this callback table; when
+ * none is installed it reads RIFF/WAVE files that already carry 11025 Hz S16 mono or
+ * stereo PCM.  All callbacks return 0 on success.
+ *   probe:   stream duration (the reference's stream/format duration, analyzer.rs:352-371)
+ *            and whether the file has video / audio streams (util.rs:41-53)
+ *   decode:  interleaved S16 at 11025 Hz of [from_ns, until_ns) (UINT64_MAX = to the
+ *            end); every file of one analyzer run must use the same channel count (1|2)
+ *   release: frees a buffer returned by decode */
+typedef struct nb200_capi_decoder {
+    void *user;
+    int (*probe)(void *user, const char *path, uint64_t *duration_ns, int *has_video, int *has_audio);
+    int (*decode)(void *user, const char *path, uint64_t from_ns, uint64_t until_ns, int16_t **pcm,
+                  uint64_t *n_samples_total, int *channels);
+    void (*release)(void *user, int16_t *pcm);
+} nb200_capi_decoder;
+/* NULL restores the built-in WAVE reader.  Exported by libneedle.so. */
+int nb200_capi_set_decoder(const nb200_capi_decoder *decoder);
+/* Read access to a FrameHashes handle of needle.h (opaque there, as in the reference):
+ * the opening (ending = 0) or ending (1) list as SoA, the hash duration and the header md5.
+ * Pointers are borrowed from the handle.  Exported by libneedle.so. */
+struct FrameHashes;
+int nb200_capi_frame_hashes_view(const struct FrameHashes *f, int ending, const uint32_t **hashes,
+                                 const uint64_t **ts_ns, uint64_t *n, uint64_t *hash_duration_ns,
+                                 const char **md5);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,11 +16,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libneedle_b200.so")
+CAPI_LIB = os.path.join(HERE, "libneedle.so")   # the needle-capi ABI (include/needle.h) over libneedle_b200.so
 OBJ_DIR = os.path.join(HERE, "_obj")
 
 SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote_device.cu", "vote.cpp", "persist.cpp"]
 HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"),
-           os.path.join(INCLUDE, "needle_b200.h")]
+           os.path.join(INCLUDE, "needle_b200.h"), os.path.join(INCLUDE, "needle.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -65,6 +66,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    # libneedle.so: host C++ only, resolves nb200_* from the library next to it
+    capi_src = os.path.join(CSRC, "capi.cpp")
+    if force or _stale(CAPI_LIB, [capi_src, LIB, __file__] + HEADERS):
+        cxx = shutil.which("g++") or "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-o", CAPI_LIB, capi_src,
+               "-L" + HERE, "-lneedle_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("libneedle.so failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(os.path.join(OBJ_DIR, "ptxas.log"), "a") as f:
         f.write("".join(log))
     return LIB

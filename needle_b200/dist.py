@@ -140,6 +140,33 @@ def globalize_runs(runs: np.ndarray, slice_start: int) -> np.ndarray:
     return runs
 
 
+def bind_host_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned
+    PCM buffers it allocates afterwards are first-touched on that NUMA node and the H2D copies
+    of several ranks do not all cross the same socket link.  Best effort: False if NVML or the
+    affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device_index]) if vis and vis.replace(",", "").isdigit() else device_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if not cpus:
+                return False
+            os.sched_setaffinity(0, cpus)
+            return True
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return False
+
+
 class GpuBackend:
     """The product compute path: libneedle_b200.so on this rank's GPU, running
     on torch's current stream so that NCCL collectives order with the kernels."""

@@ -23,7 +23,8 @@ def header_functions():
 
 
 def test_header_symbols_are_exported_and_bound():
-    names = header_functions()
+    # nb200_capi_* are the hooks of libneedle.so (tests/test_capi.py); the rest is libneedle_b200.so
+    names = [n for n in header_functions() if not n.startswith("nb200_capi_")]
     assert len(names) >= 40
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True)
     exported = set(re.findall(r" T (nb200_[a-z0-9_]+)", out.stdout))
