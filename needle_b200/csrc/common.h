@@ -180,7 +180,8 @@ struct nb200_ctx {
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
     nb200::DevBuf d_g4_twa, d_g4_twb, d_g4_base, d_g4_notes;
-    int k1_variant = 0;   // 0: one warp per frame; 4/5/6: four warps per frame, that many frames per CTA
+    int k1_variant = 0;   // 0: default (= 12); 1: 64 values per lane; 8/10/12: 32 values per lane, that many warps
+                          // per SM; 4/5/6: four warps per frame, that many frames per CTA
     nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
 

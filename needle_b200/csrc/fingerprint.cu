@@ -358,6 +358,198 @@ __global__ void __launch_bounds__(FP_WARPS * 32, 1) fp_fft_chroma_kernel(const K
 }
 
 // ---------------------------------------------------------------------------
+// K1, half-frame-in-registers variant ("h32").  The kernel above keeps all 64
+// complex values of a lane in registers (255 registers, 8 warps per SM, two per
+// scheduler) and is latency bound at 0.5 IPC.  Here a lane never holds more than
+// 32: each 64-point pass-1 FFT is split by radix 2 into its even and odd rows,
+// and pass 2 is done one 32-point FFT at a time, with the half that is not being
+// worked on parked in the warp's exchange buffer:
+//
+//   rows m = 2j   -> 32-point FFT -> E[k] parked in rows 32..63 of the buffer
+//   rows m = 2j+1 -> 32-point FFT -> O[k];  Y[k] = E[k] + W64^k O[k] -> row k,
+//                                          Y[k+32] = E[k] - W64^k O[k] -> row k+32 (over E[k])
+//   k1 = L+32: twiddle, 32-point FFT over n2 -> Z[L + 32 t], t odd, parked in rows 32..63
+//   k1 = L:    twiddle, 32-point FFT over n2 -> Z[L + 32 t], t even, in registers
+//   split: bin k = L + 32 t pairs with 2048 - k = (32 - L) + 32 (63 - t): one of the two
+//   is in registers (own, or fetched by shuffle), the other in the parked half (own
+//   slot, or read directly from the partner lane's slot -- no shuffle).
+//
+// ~100 registers -> NW = 12 warps per SM (three per scheduler); the exchange
+// buffer (16.5 KB per warp) is what bounds NW: 12 x 16.5 + 16 (twiddles) + 8
+// (window, half of it: the Hamming window is symmetric) = 222 KB of 227.
+template <int NW> constexpr int h32_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * K1_WARP_BYTES + NW * 8; }
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    f2 *s_window = reinterpret_cast<f2 *>(smem_raw);                     // 1024: first half of the window
+    f2 *s_twiddle = s_window + FP_HALF / 2;                              // 2048
+    unsigned char *s_warp = reinterpret_cast<unsigned char *>(s_twiddle + FP_HALF);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_warp + NW * K1_WARP_BYTES);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
+        if (i < FP_HALF / 2) s_window[i] = a.window[i];
+        s_twiddle[i] = a.twiddle[i];
+    }
+    if (threadIdx.x < NW) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    f2 *xchg = reinterpret_cast<f2 *>(s_warp + warp * K1_WARP_BYTES);
+    f2 *park = xchg + 32 * XCHG_STRIDE;                                  // rows 32..63
+    const uint32_t *pcm_words = reinterpret_cast<const uint32_t *>(xchg);
+    const uint32_t bar = smem_u32(s_bar + warp);
+    const uint32_t xchg_addr = smem_u32(xchg);
+    const int partner = (32 - lane) & 31;
+    const f2 lane_w = a.lane_w[lane];
+
+    const uint32_t n_blocks = (a.frame_end - a.frame_begin + NW - 1) / NW;
+    uint32_t blk = blockIdx.x;
+    uint32_t frame = a.frame_begin + blk * NW + warp;
+    uint32_t phase = 0;
+    uint32_t delta = 0;
+    if (blk < n_blocks && frame < a.frame_end) {
+        const int16_t *src = frame_src(a, frame);
+        delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        if (lane == 0) {
+            mbar_expect_tx(bar, PCM_COPY_BYTES);
+            bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+        }
+    }
+
+    for (; blk < n_blocks; blk += gridDim.x) {
+        frame = a.frame_begin + blk * NW + warp;
+        if (frame >= a.frame_end) break;   // warp-uniform; only warp-level sync below
+
+        f2 v[32];
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const uint32_t *p = pcm_words + (delta >> 2) + lane;
+        const uint32_t shift = (delta & 2) * 8;
+        // ---- pass 1: even rows (half = 0), then odd rows (half = 1).  One copy of the load and
+        //      of the 32-point FFT serves both: the kernel's code must stay inside the
+        //      instruction cache now that three warps per scheduler run at different places in it.
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            // row m = 2 j + half at lane L: PCM word 32 m + L, window w[32 m + L] for m < 32 (j < 16),
+            // else the mirrored entry w[32 (63 - m) + 31 - L], swapped
+            const uint32_t *ph = p + 32 * half;
+            const f2 *wlo = s_window + 32 * half + lane;
+            const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                const f2 s = s16x2_to_float(__funnelshift_r(w0, w1, shift));
+                const f2 wv = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                v[j] = mul2(s, wv);
+            }
+            if (half == 1) __syncwarp();   // every lane has taken its PCM: rows 0..31 may be overwritten
+            fft32(v);
+            if (half == 0) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) park[k * XCHG_STRIDE + lane] = v[pos32(k)];   // bytes >= 8448: clear of the PCM
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    const f2 o = k == 0 ? v[pos32(0)] : cmulc(v[pos32(k)], c_w64[k], c_w64r[k]);
+                    const f2 e = park[k * XCHG_STRIDE + lane];
+                    xchg[k * XCHG_STRIDE + lane] = add2(e, o);
+                    park[k * XCHG_STRIDE + lane] = sub2(e, o);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: k1 = L + 32 (q = 1: odd t, parked), then k1 = L (q = 0: even t, stays in registers)
+#pragma unroll 1
+        for (int q = 1; q >= 0; q--) {
+            const f2 *row = xchg + (lane + 32 * q) * XCHG_STRIDE;
+            const f2 *tw = s_twiddle + lane + 32 * q;
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul(row[n2], tw[n2 * 64]);
+            __syncwarp();   // this half of the rows is consumed (q = 0: and the parked half is visible)
+            if (q == 0) {
+                // rows 0..31 are free: start the next frame's PCM on its way
+                const uint32_t nblk = blk + gridDim.x;
+                const uint32_t nframe = a.frame_begin + nblk * NW + warp;
+                if (nblk < n_blocks && nframe < a.frame_end) {
+                    const int16_t *src = frame_src(a, nframe);
+                    delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+                    fence_proxy_async();
+                    if (lane == 0) {
+                        mbar_expect_tx(bar, PCM_COPY_BYTES);
+                        bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+                    }
+                }
+            }
+            fft32(v);
+            if (q == 1) {
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2++) park[k2 * XCHG_STRIDE + lane] = v[pos32(k2)];   // Z[L + 32 (2 k2 + 1)]
+            }
+        }
+        __syncwarp();
+        // Z[L + 32 t]: t even -> v[pos32(t / 2)], t odd -> park[(t - 1) / 2][L]
+
+        float acc[FP_BANDS];
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) acc[b] = 0.f;
+        // the 123 lane-range predicates of the fold depend on the lane only; read the lane id
+        // through a volatile asm so that they are recomputed here instead of being hoisted out of
+        // the frame loop and kept (spilled) for its whole body
+        int lane_s;
+        asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_s));
+        // likewise W_4096^(L + 32 t) = lane_w * W_128^t: two packed ops per bin when computed here;
+        // hoisted out of the frame loop it becomes 41 spilled values per thread (140 KB of local
+        // memory per CTA behind an L1 that shared memory has shrunk to ~30 KB)
+        f2 lw = lane_w;
+        asm volatile("" : "+f"(lw.x), "+f"(lw.y));
+#pragma unroll
+        for (int t = 0; t < FP_T; t++) {
+            f2 z, zp;
+            if ((t & 1) == 0) {
+                z = v[pos32(t >> 1)];
+                zp = park[(31 - (t >> 1)) * XCHG_STRIDE + partner];      // t' = 63 - t, odd, from the partner's slot
+                // lane 0 pairs k = 32 t with 2048 - 32 t = 32 (64 - t): even, in its own registers (t = 0: itself)
+                const f2 own = v[pos32(t == 0 ? 0 : (64 - t) >> 1)];
+                if (lane == 0) zp = own;
+            } else {
+                z = park[(t >> 1) * XCHG_STRIDE + lane];
+                const f2 ps = v[pos32((63 - t) >> 1)];                    // t' = 63 - t, even, in the partner's registers
+                zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
+                zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
+                const f2 own = park[((64 - t) >> 1) * XCHG_STRIDE];       // lane 0: t' = 64 - t, odd, parked at lane 0
+                if (lane == 0) zp = own;
+            }
+            const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+            const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+            const f2 w = cmulc(lw, c_w128[t], c_w128r[t]);
+            const f2 x = add2(e, cmul(o, w));
+            const float pw = x.x * x.x + x.y * x.y;
+#define FOLD(T, NOTE, LO, HI) \
+            if (t == T && lane_s >= LO && lane_s < HI) acc[NOTE] += pw;
+#include "fp_chroma_fold.inc"
+#undef FOLD
+        }
+        __syncwarp();   // the parked half has been read by every lane before the next frame overwrites it
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) {
+            float s = acc[b];
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            acc[b] = 0.25f * s;
+        }
+        if (lane == 0) {
+            float4 *out = reinterpret_cast<float4 *>(a.chroma + (uint64_t)frame * FP_BANDS);
+            out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            out[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K1, four-warps-per-frame variant ("g4").  The warp-per-frame kernel above keeps
 // 64 complex values per lane: 255 registers, 8 warps per SM, and ptxas has no
 // room to overlap dependent packed ops (ncu: issue active 49 %, stall "wait" 1.0).
@@ -840,6 +1032,12 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpy(ctx->d_fp_lane.p, lane_w.data(), sizeof(float2) * 32, cudaMemcpyHostToDevice));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  K1_SMEM_BYTES));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 h32_smem_bytes<12>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 h32_smem_bytes<10>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 h32_smem_bytes<8>()));
     ctx->fp_ready = true;
     return NB200_OK;
 }
@@ -956,8 +1154,20 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
             const uint32_t nf = f1 - f0;
-            if (ctx->k1_variant >= 4) {
-                const int groups = ctx->k1_variant;
+            const int variant = ctx->k1_variant == 0 ? 12 : ctx->k1_variant;   // default: h32, 12 warps per SM
+            if (variant >= 8) {
+                k1.frame_begin = f0;
+                k1.frame_end = f1;
+                const uint32_t nw = (uint32_t)variant;
+                const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
+                if (nw == 12)
+                    fp_fft_chroma_h32_kernel<12><<<grid1, 12 * 32, h32_smem_bytes<12>(), st>>>(k1);
+                else if (nw == 10)
+                    fp_fft_chroma_h32_kernel<10><<<grid1, 10 * 32, h32_smem_bytes<10>(), st>>>(k1);
+                else
+                    fp_fft_chroma_h32_kernel<8><<<grid1, 8 * 32, h32_smem_bytes<8>(), st>>>(k1);
+            } else if (variant >= 4) {
+                const int groups = variant;
                 g.frame_begin = f0;
                 g.frame_end = f1;
                 const uint32_t ggrid = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + groups - 1) / groups);
