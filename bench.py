@@ -10,12 +10,13 @@ the first 50 % and last 25 % of every episode, match all 378 pairs (openings and
 endings), vote.  One step = one pass of that path over one season per GPU.
 With N GPUs the job is a library of N such seasons (weak scaling): episodes are
 sharded over ranks for fingerprinting, the hash arrays are all-gathered once
-(NCCL), the N*378 within-season pairs are sharded over ranks for matching, runs
-return to rank 0, which votes.
+(NCCL), the N*378 within-season pairs are sharded over ranks for matching, every
+rank's runs land in one device block, the blocks are all-gathered once and rank
+0's GPU votes.
 
 Prints ONE JSON line (rank 0).  `value` = episode-pairs/s with the PCM already
 resident in HBM; `e2e` = the same through the host-buffer C-ABI call (pinned
-host PCM -> H2D -> kernels -> D2H of runs -> vote).  `--impl reference` times
+host PCM -> H2D -> kernels incl. the vote -> D2H of the result table).  `--impl reference` times
 the CPU restatement of the reference path (oracle/, all host threads): the
 reference itself is Rust and cannot be built in this image (no cargo).
 """
@@ -442,7 +443,7 @@ def run_b200(args):
         "config": {
             "workload": "28x20min season per GPU, analyze+search with endings (BASELINE configs[1]); "
                         "N GPUs = N seasons: episodes sharded for fingerprinting, one all-gather of hashes, "
-                        "within-season pairs sharded for matching, vote on rank 0",
+                        "within-season pairs sharded for matching, one all-gather of run blocks, device vote on rank 0",
             "episodes": n_videos, "minutes": args.minutes, "pairs": n_pairs_total,
             "audio_hours_fingerprinted": hours_total,
             "l2": "inputs larger than L2 (%.0f MB of PCM per GPU per step)" % (h2d_bytes / 1e6),
