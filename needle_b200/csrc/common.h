@@ -155,7 +155,8 @@ struct nb200_ctx {
     cudaStream_t stream = nullptr;     // the one in use (own or caller's)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[10] = {};           // pairs: K1, K2, K3, K4, device vote
-    cudaEvent_t ev_chunk[8] = {};      // H2D chunk landed (pipelined analyze)
+    cudaEvent_t ev_chunk[10] = {};     // [0..5] H2D chunk landed (pipelined analyze), [6] tsfill, [7] PCM guard,
+                                       // [8] match descriptors landed, [9] vote descriptors landed
     bool ev_valid[5] = {false, false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
@@ -165,8 +166,8 @@ struct nb200_ctx {
     // scratch reused across calls
     bool defer_wait = false;            // *_into fingerprint calls return without waiting for the stream
     bool host_vote = false;             // searches download the runs and vote on the host (vote.cpp) instead of on the device
-    nb200::DevBuf d_problems, d_tile_end, d_lut, d_counters, d_runs, d_segtab, d_lmin;
-    nb200::DevBuf d_problems_g, d_tile_end_g, d_lut_g;   // the general kernel's tiling of the same problems
+    nb200::DevBuf d_problems;   // the match stage's descriptor arena: segment table, run-length bounds, both tilings
+    nb200::DevBuf d_counters, d_runs;
     nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
     nb200::PinnedBuf h_fp_stage, h_vote_stage, h_results;   // one staging area per phase: nothing waits for a copy to drain
     // device vote scratch (vote_device.cu)

@@ -753,34 +753,35 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     if (want_fast) tile_tables(prob_f, (uint32_t)tiles_f, tend_f, lut_f);
     tile_tables(prob_g, (uint32_t)tiles_g, tend_g, lut_g);
 
-    // one pinned staging area for everything this call uploads; it is rewritten by the next
-    // match only, and every public entry point synchronises before it returns
+    // Everything this call uploads lives in ONE device arena mirrored by one pinned staging
+    // area: one H2D copy, issued on the copy stream so that it runs underneath whatever is
+    // still executing on the compute stream (K1/K2 of a fused analyze + search); the compute
+    // stream waits for it just before the first kernel that reads it.  Both areas are
+    // rewritten by the next match only, and every public entry point synchronises first.
     const uint32_t nseg = 2 * hs->n_videos;
-    const size_t b_tab = (size_t)nseg * sizeof(SegTab), b_lmin = (size_t)nseg * sizeof(uint32_t);
-    const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem), b_tend = (size_t)n_problems * sizeof(uint32_t);
-    const size_t b_lut_f = lut_f.size() * sizeof(uint32_t), b_lut_g = lut_g.size() * sizeof(uint32_t);
-    const size_t total = b_tab + b_lmin + 2 * (b_prob + b_tend) + b_lut_f + b_lut_g;
-    if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_segtab.reserve(b_tab) != NB200_OK ||
-        ctx->d_lmin.reserve(b_lmin) != NB200_OK || ctx->d_problems.reserve(b_prob) != NB200_OK ||
-        ctx->d_tile_end.reserve(b_tend) != NB200_OK || ctx->d_lut.reserve(std::max<size_t>(b_lut_f, 4)) != NB200_OK ||
-        ctx->d_problems_g.reserve(b_prob) != NB200_OK || ctx->d_tile_end_g.reserve(b_tend) != NB200_OK ||
-        ctx->d_lut_g.reserve(b_lut_g) != NB200_OK)
-        return NB200_ERR_CUDA;
-    char *st = ctx->h_stage.as<char>();
-    size_t pos = 0;
-    auto put = [&](void *dev, const void *src, size_t bytes) -> cudaError_t {
-        if (bytes == 0) return cudaSuccess;
-        memcpy(st + pos, src, bytes);
-        cudaError_t e = cudaMemcpyAsync(dev, st + pos, bytes, cudaMemcpyHostToDevice, s);
-        pos += bytes;
-        return e;
+    size_t total = 0;
+    auto carve = [&](size_t bytes) {
+        const size_t off = total;
+        total += (bytes + 255) & ~size_t(255);
+        return off;
     };
+    const size_t o_tab = carve((size_t)nseg * sizeof(SegTab)), o_lmin = carve((size_t)nseg * sizeof(uint32_t));
+    const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem), b_tend = (size_t)n_problems * sizeof(uint32_t);
+    const size_t o_prob_f = carve(b_prob), o_tend_f = carve(b_tend), o_lut_f = carve(lut_f.size() * sizeof(uint32_t));
+    const size_t o_prob_g = carve(b_prob), o_tend_g = carve(b_tend), o_lut_g = carve(lut_g.size() * sizeof(uint32_t));
+    if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_problems.reserve(total) != NB200_OK) return NB200_ERR_CUDA;
+    char *st = ctx->h_stage.as<char>();
+    char *arena = ctx->d_problems.as<char>();
+    SegTab *const d_segtab = reinterpret_cast<SegTab *>(arena + o_tab);
+    uint32_t *const d_lmin = reinterpret_cast<uint32_t *>(arena + o_lmin);
+    MatchProblem *const d_prob_f = reinterpret_cast<MatchProblem *>(arena + o_prob_f);
+    MatchProblem *const d_prob_g = reinterpret_cast<MatchProblem *>(arena + o_prob_g);
 
     // run-length lower bounds per segment, computed where the timestamps live
     uint32_t max_len = 1;
     {
-        std::vector<SegTab> tab(nseg);
-        std::vector<uint32_t> init(nseg);
+        SegTab *tab = reinterpret_cast<SegTab *>(st + o_tab);
+        uint32_t *init = reinterpret_cast<uint32_t *>(st + o_lmin);
         for (uint32_t k = 0; k < nseg; k++) {
             tab[k] = {hs->dev_offset[k], hs->seg_len[k]};
             const uint64_t mn = (k & 1) ? params->min_ending_ns : params->min_opening_ns;
@@ -788,25 +789,25 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
             init[k] = (hs->seg_len[k] < 2 || mn == 0) ? 1u : std::min<uint32_t>(hs->seg_len[k], 0x7fffffffu);
             max_len = std::max(max_len, hs->seg_len[k]);
         }
-        NB_CUDA(put(ctx->d_segtab.p, tab.data(), b_tab));
-        NB_CUDA(put(ctx->d_lmin.p, init.data(), b_lmin));
     }
+    if (want_fast) {
+        memcpy(st + o_prob_f, prob_f.data(), b_prob);
+        memcpy(st + o_tend_f, tend_f.data(), b_tend);
+        memcpy(st + o_lut_f, lut_f.data(), lut_f.size() * sizeof(uint32_t));
+    }
+    memcpy(st + o_prob_g, prob_g.data(), b_prob);
+    memcpy(st + o_tend_g, tend_g.data(), b_tend);
+    memcpy(st + o_lut_g, lut_g.data(), lut_g.size() * sizeof(uint32_t));
+    NB_CUDA(cudaMemcpyAsync(arena, st, total, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NB_CUDA(cudaEventRecord(ctx->ev_chunk[8], ctx->copy_stream));
+    NB_CUDA(cudaStreamWaitEvent(s, ctx->ev_chunk[8], 0));
+
     seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
-        hs->d_ts.as<uint64_t>(), ctx->d_segtab.as<SegTab>(), params->min_opening_ns, params->min_ending_ns,
-        ctx->d_lmin.as<uint32_t>());
+        hs->d_ts.as<uint64_t>(), d_segtab, params->min_opening_ns, params->min_ending_ns, d_lmin);
     NB_CUDA(cudaGetLastError());
     ctx->n_launches++;
-    if (want_fast) {
-        NB_CUDA(put(ctx->d_problems.p, prob_f.data(), b_prob));
-        NB_CUDA(put(ctx->d_tile_end.p, tend_f.data(), b_tend));
-        NB_CUDA(put(ctx->d_lut.p, lut_f.data(), b_lut_f));
-    }
-    NB_CUDA(put(ctx->d_problems_g.p, prob_g.data(), b_prob));
-    NB_CUDA(put(ctx->d_tile_end_g.p, tend_g.data(), b_tend));
-    NB_CUDA(put(ctx->d_lut_g.p, lut_g.data(), b_lut_g));
-    problem_finalize_kernel<<<(n_problems + 255) / 256, 256, 0, s>>>(
-        want_fast ? ctx->d_problems.as<MatchProblem>() : nullptr, ctx->d_problems_g.as<MatchProblem>(),
-        ctx->d_lmin.as<uint32_t>(), n_problems, ctx->d_counters.as<unsigned int>());
+    problem_finalize_kernel<<<(n_problems + 255) / 256, 256, 0, s>>>(want_fast ? d_prob_f : nullptr, d_prob_g, d_lmin,
+                                                                      n_problems, ctx->d_counters.as<unsigned int>());
     NB_CUDA(cudaGetLastError());
     ctx->n_launches++;
 
@@ -822,9 +823,9 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     };
     NB_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (want_fast) {
-        args.problems = ctx->d_problems.as<MatchProblem>();
-        args.tile_end = ctx->d_tile_end.as<uint32_t>();
-        args.lut = ctx->d_lut.as<uint32_t>();
+        args.problems = d_prob_f;
+        args.tile_end = reinterpret_cast<const uint32_t *>(arena + o_tend_f);
+        args.lut = reinterpret_cast<const uint32_t *>(arena + o_lut_f);
         args.n_tiles = (uint32_t)tiles_f;
         args.mode = 1;
         if (ctx->match_dense)
@@ -834,9 +835,9 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
     }
-    args.problems = ctx->d_problems_g.as<MatchProblem>();
-    args.tile_end = ctx->d_tile_end_g.as<uint32_t>();
-    args.lut = ctx->d_lut_g.as<uint32_t>();
+    args.problems = d_prob_g;
+    args.tile_end = reinterpret_cast<const uint32_t *>(arena + o_tend_g);
+    args.lut = reinterpret_cast<const uint32_t *>(arena + o_lut_g);
     args.n_tiles = (uint32_t)tiles_g;
     args.mode = want_fast ? 2 : 0;
     match_kernel<<<grid_for(tiles_g), MATCH_WARPS * 32, 0, s>>>(args);
@@ -847,7 +848,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
 
     NB_CUDA(cudaEventRecord(ctx->ev[6], s));
     simhash_kernel<<<(uint32_t)ctx->sm_count * 2, 128, 0, s>>>(hs->d_hashes.as<uint32_t>(),
-                                                             ctx->d_problems_g.as<MatchProblem>(), runs_out,
+                                                             d_prob_g, runs_out,
                                                              ctx->d_counters.as<unsigned int>(), run_cap);
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaEventRecord(ctx->ev[7], s));

@@ -303,17 +303,19 @@ int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_
         ctx->h_vote_stage.reserve((upload_csr ? b_csr : 0) + b_hd) != NB200_OK ||
         ctx->h_results.reserve(b_res + 16) != NB200_OK)
         return NB200_ERR_CUDA;
-    // d_vote_csr may just have been reallocated by reserve(): then the cached copy is gone
+    // CSR (unless the device already holds it) and hash durations: one staging area, copied on
+    // the copy stream underneath the match kernels; the compute stream waits before the vote
     char *st = ctx->h_vote_stage.as<char>();
-    size_t pos = 0;
     if (upload_csr) {
         memcpy(st, csr->data(), b_csr);
-        NB_CUDA(cudaMemcpyAsync(ctx->d_vote_csr.p, st, b_csr, cudaMemcpyHostToDevice, s));
-        pos = b_csr;
+        NB_CUDA(cudaMemcpyAsync(ctx->d_vote_csr.p, st, b_csr, cudaMemcpyHostToDevice, ctx->copy_stream));
         if (default_list) ctx->vote_csr_on_device = true;
     }
-    memcpy(st + pos, hash_duration_ns, b_hd);
-    NB_CUDA(cudaMemcpyAsync(ctx->d_vote_hd.p, st + pos, b_hd, cudaMemcpyHostToDevice, s));
+    memcpy(st + (upload_csr ? b_csr : 0), hash_duration_ns, b_hd);
+    NB_CUDA(cudaMemcpyAsync(ctx->d_vote_hd.p, st + (upload_csr ? b_csr : 0), b_hd, cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+    NB_CUDA(cudaEventRecord(ctx->ev_chunk[9], ctx->copy_stream));
+    NB_CUDA(cudaStreamWaitEvent(s, ctx->ev_chunk[9], 0));
 
     VoteArgs a;
     a.runs = d_runs;

@@ -129,3 +129,19 @@ def test_pcmset_search_equals_two_calls(ctx):
     assert one == two
     assert ctx.analyze_search(segs, 1, seeks, synth.HASH_DURATION_NS, p) == two
     assert sum(r[1] for r in one) == 4
+
+
+def test_200_video_library_device_equals_host_vote(ctx):
+    """BASELINE configs[3] shapes (200 x 24 min: 19,900 pairs, 39,800 tables, ~400 candidates per
+    video): too slow for the oracle's table fill, so the two independent votes of the library (GPU
+    kernels, host C++) are checked against each other, and against the planted structure."""
+    season = synth.make_hash_season(200, 2897, 1443, seed=4)
+    p = engine.match_params(include_endings=True)
+    dev, host, dev_ms, _ = searches(ctx, season, p)
+    assert dev == host
+    assert sum(r[1] for r in dev) >= 190 and sum(r[2] for r in dev) >= 190   # occasional hard breaks split a plant
+    assert 0.0 < dev_ms < 5.0
+    # what is found is (a piece of) the planted run: at most 366 hashes of 0.246 s, at least the 20 s minimum
+    for r in dev:
+        if r[1]:
+            assert 19e9 < r[4] - r[3] < 95e9
