@@ -10,7 +10,7 @@ rng = np.random.default_rng(0)
 lens = [0, 4095, 4096, 4096 + 1365 * 19, 4096 + 1365 * 40 + 7, 60_001, 90_000, 33_333]
 segs = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
 ref = None
-for variant in (0, 4, 5, 6):
+for variant in (0, 1, 4, 5, 6, 8, 10):
     ctx.set_option(2, variant)
     out = ctx.fingerprint_batch(segs)
     if ref is None:
@@ -29,4 +29,24 @@ for params in (engine.match_params(include_endings=True),
                engine.match_params(include_endings=True, min_opening_ns=0, min_ending_ns=10 ** 9, threshold=12)):
     runs = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, params)
     ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
+# device vote vs host vote, the PCM-resident fused call, run blocks (export -> vote_blocks)
+hs = engine.HashSet.upload(ctx, season.hashes, season.ts_ns, season.seg_offset)
+for params in (engine.match_params(include_endings=True),
+               engine.match_params(include_endings=True, min_opening_ns=10 ** 9, min_ending_ns=10 ** 9, threshold=12)):
+    dev = hs.search(season.hash_duration_ns, params)
+    ctx.set_option(4, 1)
+    host = hs.search(season.hash_duration_ns, params)
+    ctx.set_option(4, 0)
+    assert dev == host
+import torch
+block = 64 * (1 + 256)
+buf = torch.zeros(2 * block, dtype=torch.uint8, device="cuda:0")
+pairs = np.array([(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)], np.uint32)
+params = engine.match_params(include_endings=True)
+hs.match_export(params, pairs[:3], 0, buf.data_ptr(), block)
+hs.match_export(params, pairs[3:], 3, buf.data_ptr() + block, block)
+got, found, trunc = ctx.vote_blocks(buf.data_ptr(), 2, block, season.hash_duration_ns, params)
+assert not trunc and got == hs.search(season.hash_duration_ns, params)
+ps = engine.PcmSet.upload(ctx, [segs[6], segs[5], segs[6], segs[7], segs[5], segs[7]])
+assert ps.search(None, synth.HASH_DURATION_NS, p) == res
 print("sanitize target ok", len(runs), res[:1])
