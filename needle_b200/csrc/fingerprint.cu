@@ -1194,14 +1194,16 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
             // may still read the (pooled) PCM buffer
             NB_CUDA_F(cudaEventRecord(ctx->ev_chunk[7], st));
             NB_CUDA_F(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[7], 0));
-            // chunks of consecutive segments, ~equal bytes
+            // chunks of consecutive segments, shrinking towards the end: the copy is the long pole
+            // (PCIe), so what matters is how little K1 work is left when the last byte lands
             constexpr int N_CHUNKS = 6;
+            static const uint32_t CUM_PERMILLE[N_CHUNKS] = {300, 550, 750, 880, 960, 1000};
             uint64_t total_mono = 0;
             for (uint32_t s2 = 0; s2 < nseg; s2++) total_mono += ps->n_mono[s2];
             uint32_t seg = 0;
             uint64_t done = 0;
             for (int c = 0; c < N_CHUNKS && seg < nseg; c++) {
-                const uint64_t target = total_mono * (uint64_t)(c + 1) / N_CHUNKS;
+                const uint64_t target = total_mono / 1000 * CUM_PERMILLE[c];
                 const uint32_t first = seg;
                 while (seg < nseg && (done < target || c == N_CHUNKS - 1)) {
                     if (ps->n_mono[seg] > 0)

@@ -77,3 +77,50 @@ def test_gpu_runs_equal_oracle_property(ctx, oracle, case):
     want = H.oracle_pair_runs(oracle, season, **kw)
     got = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, engine.match_params(**kw))
     assert H.runs_as_rows(got) == want
+
+
+@st.composite
+def vote_case(draw):
+    """Small seasons over a tiny hash alphabet: many equal runs, equal signatures and equal
+    durations, i.e. the ties that candidate order and heap order decide."""
+    n_videos = draw(st.integers(2, 6))
+    alphabet = draw(st.lists(st.integers(0, 2 ** 32 - 1), min_size=1, max_size=3))
+    openings, endings = [], []
+    for _ in range(n_videos):
+        no = draw(st.integers(2, 160))
+        ne = draw(st.integers(1, 60))
+        openings.append((hash_list(draw, no, alphabet, True), synth.hash_timestamps(2 * no, 2)[:no]))
+        endings.append((hash_list(draw, ne, alphabet, True), synth.hash_timestamps(2 * ne, 2, seek_to_ns=10 ** 12)[:ne]))
+    thr = draw(st.sampled_from([0, 1, 3, 10]))
+    mn = draw(st.sampled_from([10 ** 9, 3 * 10 ** 9, 8 * 10 ** 9]))
+    pad = draw(st.sampled_from([0, 0, 250_000_000, 10 ** 9]))
+    hd = [draw(st.sampled_from([300_000_012, 123_000_000, 10 ** 9])) for _ in range(n_videos)]
+    return openings, endings, thr, mn, pad, hd
+
+
+@pytest.mark.gpu
+@settings(max_examples=40, **SETTINGS)
+@given(vote_case())
+def test_gpu_vote_equals_oracle_property(ctx, oracle, case):
+    """Final per-video intervals of the device vote (and of the host vote) against the oracle's
+    find_best_match, bit for bit, including the reference's panic cases as an error status."""
+    from needle_b200._lib import ERR_DURATION_UNDERFLOW, OPT_HOST_VOTE, Nb200Error
+    openings, endings, thr, mn, pad, hd = case
+    season = H.season_from_lists(openings, endings)
+    season.hash_duration_ns[:] = np.asarray(hd, np.uint64)
+    kw = H.params_kw(threshold=thr, include_endings=True, min_opening_ns=mn, min_ending_ns=mn // 2, time_padding_ns=pad)
+    st_, want, _ = H.oracle_run(oracle, season, **kw)
+    p = engine.match_params(**kw)
+    hs = engine.HashSet.upload(ctx, season.hashes, season.ts_ns, season.seg_offset)
+    try:
+        for host_vote in (0, 1):
+            ctx.set_option(OPT_HOST_VOTE, host_vote)
+            try:
+                got = hs.search(season.hash_duration_ns, p)
+                assert st_ == 0 and got == want
+            except Nb200Error as e:
+                # end - padding - hash_duration underflows: a panic in the reference, a status here
+                assert e.status == ERR_DURATION_UNDERFLOW and st_ != 0
+    finally:
+        ctx.set_option(OPT_HOST_VOTE, 0)
+        hs.free()
