@@ -47,6 +47,7 @@ constexpr int DST_TILE = MATCH_R + MATCH_DW + 8;  // cols tile_j0 .. tile_j0+R+2
 constexpr int LUT_SHIFT = 7;
 constexpr int FAST_DST_TILE = 2 * MATCH_R;        // fast kernel: s = 255 + kk - x in [0, 510]
 constexpr int FOREIGN = -(1 << 30);   // carry marker: run started in an earlier chunk
+constexpr int COOP_MAX_LANES = 8;     // fast kernel: at most this many lanes alive -> verify their words cooperatively
 
 struct MatchProblem {
     uint32_t src_off, n;    // element offset into d_hashes / d_ts, length
@@ -395,6 +396,45 @@ __device__ __noinline__ void coop_long_run(const EmitCtx a, uint32_t problem, in
     if (lane == 0) check_emit(a, problem, i_first + len - 1, d, len);
 }
 
+// A full word (32 matching cells of wrapped diagonal u = ub + x starting at row i0) was found:
+// drop the look-alikes the wrapped tiling can produce, then let the warp walk the run.
+__device__ __forceinline__ void full_word(const EmitCtx &ectx, uint32_t p, int i0, int u, int M, int n, int lane) {
+    if (u >= M || i0 == 0 || i0 + 31 > n - 1) return;     // duplicate diagonal / row 0 / past the end
+    int jm = (i0 - 1 - u) % M;                              // j0 - 1
+    if (jm < 0) jm += M;
+    if (jm + 31 > M - 1) return;                            // the wrap point is inside the word
+    coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
+}
+
+// Few diagonals of this 32-row word are still alive after a sampling stage: instead of running
+// the remaining stages over all 256 diagonals of the tile, the warp tests each survivor's whole
+// word at once -- lane r takes row r -- which is exact ("all 32 cells match") and costs a dozen
+// instructions per survivor against ~90 per stage.  On real audio unrelated frames of stationary
+// background match with p ~ 0.15-0.2 and neighbouring cells of a diagonal correlate (0.4 at 8
+// rows), so a word rarely dies in the first stage.  Measured on the bench season
+// (profiles/r01_ncu_k3_match_real_v4.txt): stage 1 runs for 66 % of the words, stage 2 for 31 %,
+// later stages for < 4 %; this path takes the others.  It is a serial chain per survivor
+// (load, XOR, POPC, vote), so it only pays for a handful: with 16 lanes alive it loses to
+// another stage.
+__device__ __noinline__ void coop_verify(const EmitCtx ectx, uint32_t p, const uint32_t *src_t, const uint32_t *dst_t,
+                                         int step, int i0, int ub, int M, int n, uint32_t lanes_alive, uint32_t mine,
+                                         int lane) {
+    const uint32_t sv = src_t[32 * step + lane];
+    while (lanes_alive) {
+        const int sl = __ffs((int)lanes_alive) - 1;
+        lanes_alive &= lanes_alive - 1;
+        uint32_t f = __shfl_sync(0xffffffffu, mine, sl);
+        while (f) {
+            const int c = __ffs((int)f) - 1;
+            f &= f - 1;
+            const int x = sl * MATCH_C + c;
+            // cell (row 32 step + lane, diagonal x) <-> dst_t[255 + 32 step + lane - x]
+            const bool ok = __popc(sv ^ dst_t[255 + 32 * step + lane - x]) <= (int)ectx.threshold;
+            if (__all_sync(0xffffffffu, ok)) full_word(ectx, p, i0, ub + x, M, n, lane);
+        }
+    }
+}
+
 //
 // Geometry: diagonals are WRAPPED modulo (m - 1).  Column 0 never matches, so a
 // row has m - 1 live columns j = 1 .. m-1; wrapped diagonal u holds the cells
@@ -501,7 +541,15 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                             int b2 = mx[0];
 #pragma unroll
                             for (int c = 1; c < MATCH_C; c++) b2 = min(b2, mx[c]);
-                            alive = __any_sync(0xffffffffu, b2 <= T);
+                            const uint32_t lanes_alive = __ballot_sync(0xffffffffu, b2 <= T);
+                            alive = lanes_alive != 0;
+                            if (stage < 3 && alive && __popc(lanes_alive) <= COOP_MAX_LANES) {
+                                uint32_t mine = 0;
+#pragma unroll
+                                for (int c = 0; c < MATCH_C; c++) mine |= (mx[c] <= T ? 1u : 0u) << c;
+                                coop_verify(ectx, p, src_t, dst_t, step, r0 + 32 * step, ub, M, n, lanes_alive, mine, lane);
+                                alive = false;   // this word is done
+                            }
                         }
                     }
                 }
@@ -551,12 +599,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                 while (f) {
                     const int c = __ffs((int)f) - 1;
                     f &= f - 1;
-                    const int u = ub + src_lane * MATCH_C + c;
-                    if (u >= M || i0 == 0 || i0 + 31 > n - 1) continue;     // duplicate diagonal / row 0 / past the end
-                    int jm = (i0 - 1 - u) % M;                              // j0 - 1
-                    if (jm < 0) jm += M;
-                    if (jm + 31 > M - 1) continue;                          // the wrap point is inside the word
-                    coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
+                    full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, M, n, lane);
                 }
             }
         }
