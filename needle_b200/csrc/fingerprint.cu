@@ -79,6 +79,13 @@ __device__ __forceinline__ f2 by(f2 a) { return make_float2(a.y, a.y); }
 __device__ __forceinline__ f2 swp(f2 a) { return make_float2(a.y, a.x); }
 // a * w for a run-time w
 __device__ __forceinline__ f2 cmul(f2 a, f2 w) { return fma2(by(a), make_float2(-w.y, w.x), mul2(bx(a), w)); }
+// a * w in three packed instructions and nothing else: P = a.x * w, Q = a.y * (w.y, w.x),
+// result = P + (-Q.x, Q.y) -- the (-1, 1) factor becomes an operand modifier.  cmul() above
+// needs a scalar negation and a register move to build (-w.y, w.x) from a run-time w.
+__device__ __forceinline__ f2 cmul3(f2 a, f2 w) {
+    const f2 q = mul2(by(a), swp(w));
+    return fma2(q, make_float2(-1.f, 1.f), mul2(bx(a), w));
+}
 // a * w with wr = (-w.y, w.x) supplied (tables of constants carry both forms)
 __device__ __forceinline__ f2 cmulc(f2 a, f2 w, f2 wr) { return fma2(by(a), wr, mul2(bx(a), w)); }
 // d + (-i) t   and   d - (-i) t
@@ -476,7 +483,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
             const f2 *row = xchg + (lane + 32 * q) * XCHG_STRIDE;
             const f2 *tw = s_twiddle + lane + 32 * q;
 #pragma unroll
-            for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul(row[n2], tw[n2 * 64]);
+            for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul3(row[n2], tw[n2 * 64]);
             __syncwarp();   // this half of the rows is consumed (q = 0: and the parked half is visible)
             if (q == 0) {
                 // rows 0..31 are free: start the next frame's PCM on its way
@@ -534,7 +541,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
             const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
             const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
             const f2 w = cmulc(lw, c_w128[t], c_w128r[t]);
-            const f2 x = add2(e, cmul(o, w));
+            const f2 x = add2(e, cmul3(o, w));
             const float pw = x.x * x.x + x.y * x.y;
 #define FOLD(T, NOTE, LO, HI) \
             if (t == T && lane_s >= LO && lane_s < HI) acc[NOTE] += pw;
