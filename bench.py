@@ -432,7 +432,7 @@ def run_b200(args):
     traffic, traffic_src = None, None
     if args.episodes == EPISODES and args.minutes == MINUTES:
         if dominant == "fp_fft_chroma":
-            traffic, traffic_src = 555.75e6 + 12.52e6, "profiles/r01_ncu_k1_h32_v3.txt"
+            traffic, traffic_src = 555.75e6 + 13.21e6, "profiles/r01_ncu_k1_h32_v4.txt"
         else:
             traffic, traffic_src = 0.56e6, "profiles/r01_ncu_k3_match_fast_v2.txt"
     line = {
