@@ -282,3 +282,93 @@ def test_search_analyze_in_place_and_missing_data(tmp_path, capfd):
     assert L.needle_audio_comparator_new(cp, len(paths), True, 10, 20, 20, 0.0, C.byref(c)) == capi.OK
     assert L.needle_audio_comparator_run(c, True, False, False, False, True) == capi.UNKNOWN
     L.needle_audio_comparator_free(c)
+
+
+@pytest.mark.gpu
+def test_custom_decoder_callback(tmp_path, capfd):
+    """nb200_capi_set_decoder: the host supplies decoded audio (what FFmpeg + swresample do in
+    needle, analyzer.rs:170-283) for files the library cannot read itself.  Here the "videos" are
+    .mkv files holding only an EBML signature; the PCM comes from this process."""
+    from needle_b200 import audio, synth
+    L = capi.lib()
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    eps = synth.make_pcm_season(3, 3.0, season_seed=5, intro_s=40.0, credits_s=30.0)
+    rng = np.random.default_rng(2)
+    pcm_of, paths = {}, []
+    for k, ep in enumerate(eps):
+        p = tmp_path / ("ep%d.mkv" % k)
+        p.write_bytes(bytes([0x1A, 0x45, 0xDF, 0xA3]) + rng.integers(0, 256, 9000, dtype=np.uint8).tobytes())
+        pcm_of[os.fsencode(str(p))] = ep.pcm
+        paths.append(str(p))
+    calls = {"probe": 0, "decode": 0, "release": 0}
+
+    PROBE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int))
+    DECODE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p),
+                         C.POINTER(C.c_uint64), C.POINTER(C.c_int))
+    RELEASE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+    def probe(_user, path, duration_ns, has_video, has_audio):
+        calls["probe"] += 1
+        if path not in pcm_of:
+            return 1
+        duration_ns[0] = pcm_of[path].size * 10 ** 9 // 11025
+        has_video[0], has_audio[0] = 1, 1
+        return 0
+
+    def decode(_user, path, from_ns, until_ns, pcm, n, channels):
+        calls["decode"] += 1
+        x = pcm_of[path]
+        a = min(x.size, from_ns * 11025 // 10 ** 9)
+        b = x.size if until_ns == 2 ** 64 - 1 else min(x.size, until_ns * 11025 // 10 ** 9)
+        part = np.ascontiguousarray(x[a:b])
+        buf = libc.malloc(max(part.nbytes, 2))
+        C.memmove(buf, part.ctypes.data, part.nbytes)
+        pcm[0], n[0], channels[0] = buf, part.size, 1
+        return 0
+
+    def release(_user, p):
+        calls["release"] += 1
+        libc.free(p)
+
+    class Decoder(C.Structure):
+        _fields_ = [("user", C.c_void_p), ("probe", PROBE), ("decode", DECODE), ("release", RELEASE)]
+    dec = Decoder(None, PROBE(probe), DECODE(decode), RELEASE(release))
+    assert L.nb200_capi_set_decoder(C.byref(dec)) == 0
+    try:
+        cp = capi.c_paths(paths)
+        vids, n = C.POINTER(C.c_char_p)(), C.c_size_t()
+        assert L.needle_util_find_video_files(capi.c_paths([str(tmp_path)]), 1, True, True, C.byref(vids),
+                                              C.byref(n)) == capi.OK
+        assert sorted(vids[k].decode() for k in range(n.value)) == sorted(paths)
+        L.needle_util_video_files_free(vids, n.value)
+        a = C.c_void_p()
+        assert L.needle_audio_analyzer_new(cp, 3, 0.5, 0.25, True, False, True, C.byref(a)) == capi.OK
+        assert L.needle_audio_analyzer_run(a, 0.3, True, True) == capi.OK
+        assert calls["decode"] == 6 and calls["release"] == 6      # opening + ending per video
+        # the same PCM through the library's batched fingerprint API: identical hashes
+        for k, ep in enumerate(eps):
+            # the segments Analyzer::run_single asks for (analyzer.rs:378-402), in samples
+            n_s = ep.pcm.size
+            dur = n_s * 10 ** 9 // 11025
+            n_open = min(n_s, audio.duration_mul_f32(dur, 0.5) * 11025 // 10 ** 9)
+            s_end = min(n_s, audio.duration_mul_f32(dur, np.float32(1.0) - np.float32(0.25)) * 11025 // 10 ** 9)
+            o, e = ep.pcm[:n_open], ep.pcm[s_end:]
+            with audio.engine.Context(-1) as ctx:
+                want = ctx.fingerprint_batch([o, e])
+            fh = C.c_void_p()
+            assert L.needle_audio_analyzer_get_frame_hashes(a, k, C.byref(fh)) == capi.OK
+            assert capi.frame_hashes(fh, False)[0] == want[0][::2].tolist()
+            assert capi.frame_hashes(fh, True)[0] == want[1][::2].tolist()
+        L.needle_audio_analyzer_free(a)
+        c = C.c_void_p()
+        assert L.needle_audio_comparator_new(cp, 3, True, 10, 20, 20, 0.0, C.byref(c)) == capi.OK
+        capfd.readouterr()
+        assert L.needle_audio_comparator_run(c, False, True, False, False, True) == capi.OK
+        out = capfd.readouterr().out
+        assert out.count('* Opening - "') == 3 and out.count('* Ending - "') == 3
+        L.needle_audio_comparator_free(c)
+    finally:
+        assert L.nb200_capi_set_decoder(None) == 0
