@@ -549,18 +549,36 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
 #undef FOLD
         }
         __syncwarp();   // the parked half has been read by every lane before the next frame overwrites it
+        // 12 sums over 32 lanes with halving butterflies: after the exchange over lane bit 4 a lane
+        // keeps 6 of the classes, after bit 3 it keeps 3, and only those 3 go through the last
+        // three steps -- 18 shuffles instead of 60.  Lanes 0, 8, 16, 24 end up with 3 classes each.
+        float r6[6], r3[3];
+        {
+            const bool up = (lane & 16) != 0;
 #pragma unroll
-        for (int b = 0; b < FP_BANDS; b++) {
-            float s = acc[b];
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            acc[b] = 0.25f * s;
+            for (int i = 0; i < 6; i++) {
+                const float keep = up ? acc[i + 6] : acc[i], send = up ? acc[i] : acc[i + 6];
+                r6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
         }
-        if (lane == 0) {
-            float4 *out = reinterpret_cast<float4 *>(a.chroma + (uint64_t)frame * FP_BANDS);
-            out[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            out[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            out[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+        {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float keep = up ? r6[i + 3] : r6[i], send = up ? r6[i] : r6[i + 3];
+                r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) r3[i] += __shfl_xor_sync(0xffffffffu, r3[i], o);
+        }
+        if ((lane & 7) == 0) {
+            float *out = a.chroma + (uint64_t)frame * FP_BANDS + 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1);
+            out[0] = 0.25f * r3[0];
+            out[1] = 0.25f * r3[1];
+            out[2] = 0.25f * r3[2];
         }
     }
 }
