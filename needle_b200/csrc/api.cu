@@ -151,7 +151,7 @@ int nb200_ctx_create(int device, nb200_ctx **out) {
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; ok && k < 10; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
-    for (int k = 0; ok && k < 10; k++)
+    for (int k = 0; ok && k < 12; k++)
         ok = cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && ctx->h_small.reserve(256) == NB200_OK;
     if (!ok) {
@@ -170,7 +170,7 @@ void nb200_ctx_destroy(nb200_ctx *ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     for (int k = 0; k < 10; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-    for (int k = 0; k < 10; k++)
+    for (int k = 0; k < 12; k++)
         if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -155,8 +155,10 @@ struct nb200_ctx {
     cudaStream_t stream = nullptr;     // the one in use (own or caller's)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[10] = {};           // pairs: K1, K2, K3, K4, device vote
-    cudaEvent_t ev_chunk[10] = {};     // [0..5] H2D chunk landed (pipelined analyze), [6] tsfill, [7] PCM guard,
-                                       // [8] match descriptors landed, [9] vote descriptors landed
+    cudaEvent_t ev_chunk[12] = {};     // [0..5] H2D chunk landed (pipelined analyze), [6] tsfill, [7] PCM guard,
+                                       // [8] match descriptors landed, [9] vote descriptors landed,
+                                       // [10] the last enqueued match stage (arena + staging readers) is done,
+                                       // [11] the last enqueued fingerprint stage is done
     bool ev_valid[5] = {false, false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset

@@ -1163,6 +1163,8 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         if (ctx->d_fp_desc.reserve(b_seg) != NB200_OK || ctx->h_fp_stage.reserve(b_seg) != NB200_OK ||
             ctx->d_chroma.reserve((size_t)(frames + 8) * FP_BANDS * sizeof(float)) != NB200_OK)
             return fail(NB200_ERR_CUDA);
+        // a deferred-wait call may still be reading the staging area and the chroma scratch
+        NB_CUDA_F(cudaEventSynchronize(ctx->ev_chunk[11]));
         memcpy(ctx->h_fp_stage.p, segs.data(), b_seg);
         NB_CUDA_F(cudaMemcpyAsync(ctx->d_fp_desc.p, ctx->h_fp_stage.p, b_seg, cudaMemcpyHostToDevice, st));
 
@@ -1278,6 +1280,7 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         }
         // the caller's PCM (pipelined copy) and h_fp_stage are free again once the stream drains; a
         // caller that goes on to search the season on the same stream waits once, at the very end
+        NB_CUDA_F(cudaEventRecord(ctx->ev_chunk[11], st));
         if (wait) NB_CUDA_F(cudaStreamSynchronize(st));
     }
 #undef NB_CUDA_F

@@ -812,6 +812,10 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem), b_tend = (size_t)n_problems * sizeof(uint32_t);
     const size_t o_prob_f = carve(b_prob), o_tend_f = carve(b_tend), o_lut_f = carve(lut_f.size() * sizeof(uint32_t));
     const size_t o_prob_g = carve(b_prob), o_tend_g = carve(b_tend), o_lut_g = carve(lut_g.size() * sizeof(uint32_t));
+    // The arena and the staging area are rewritten below, from another stream: the previous match
+    // stage enqueued on this context must be through with them.  Normally it is (every search
+    // ends with a synchronisation); two nb200_match_export calls back to back are the exception.
+    NB_CUDA(cudaEventSynchronize(ctx->ev_chunk[10]));
     if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_problems.reserve(total) != NB200_OK) return NB200_ERR_CUDA;
     char *st = ctx->h_stage.as<char>();
     char *arena = ctx->d_problems.as<char>();
@@ -895,6 +899,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
                                                              ctx->d_counters.as<unsigned int>(), run_cap);
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaEventRecord(ctx->ev[7], s));
+    NB_CUDA(cudaEventRecord(ctx->ev_chunk[10], s));
     ctx->ev_valid[3] = true;
     ctx->n_launches++;
     return NB200_OK;
