@@ -191,6 +191,10 @@ class GpuBackend:
     def _on_stream(self):
         return self.torch.cuda.stream(self.stream)
 
+    def upload_hashes(self, hashes, ts_ns, seg_offset):
+        """A whole library of precomputed hashes (KB..MB) on this rank's GPU."""
+        return self.engine.HashSet.upload(self.ctx, hashes, ts_ns, seg_offset)
+
     def upload_pcm(self, segments):
         return self.engine.PcmSet.upload(self.ctx, segments)
 
@@ -297,6 +301,76 @@ def unpack_run_blocks(buf: np.ndarray, counts, block: int) -> np.ndarray:
     return np.frombuffer(np.concatenate(parts).tobytes(), dtype=RUN_DTYPE)
 
 
+def search_tail(job, season, n_videos: int, t):
+    """What every rank does once it holds the whole season: match its slice of the pair list,
+    bring the runs together, vote.  Device-resident when the backend offers it (run blocks, one
+    all-gather, vote on rank 0's GPU); otherwise the generic form: runs to the host, gathered,
+    every rank votes for the videos v with v % world == rank, rank 0 collects the rows."""
+    b = job.backend
+    start, end = job.slices[job.rank]
+    if job.world > 1 and hasattr(b, "search_gathered"):
+        results = b.search_gathered(job.dist, season, job.params, job.pairs[start:end], start,
+                                    None if job._all_pairs else job.pairs, job.hash_duration_ns, job.slices,
+                                    job.group)
+        b.release(season)
+        job._tick("match+gather+vote", t)
+        return results
+    runs = globalize_runs(b.match(season, job.params, job.pairs[start:end]), start)
+    b.release(season)
+    t = job._tick("match", t)
+    all_runs = b.gather_runs(job.dist, runs, job.group) if job.world > 1 else runs
+    t = job._tick("gather_runs", t)
+    if job.world == 1:
+        table = b.vote(job.hash_duration_ns, job.params, all_runs, job.pairs)
+        job._tick("vote", t)
+        return results_rows_as_tuples(table)
+    mask = np.zeros(n_videos, np.uint8)
+    mask[job.rank::job.world] = 1
+    table = b.vote(job.hash_duration_ns, job.params, all_runs, job.pairs, video_mask=mask)
+    t = job._tick("vote", t)
+    cap = (n_videos + job.world - 1) // job.world
+    rows = b.gather_results(job.dist, table[job.rank::job.world], cap, job.group)
+    if job.rank != 0:
+        return None
+    full = np.zeros(n_videos, dtype=RESULT_DTYPE)
+    for r in range(job.world):
+        k = len(range(r, n_videos, job.world))
+        full[r::job.world] = rows[r, :k]
+    job._tick("gather_results", t)
+    return results_rows_as_tuples(full)
+
+
+class SearchJob:
+    """`needle search` from precomputed frame hashes (.needle.dat) across the ranks of a process
+    group: every rank is given the same season (it is KB..MB), matches its n*m-balanced slice of
+    the pair list and the tail of SeasonJob does the rest.  Rank 0 receives the per-video results."""
+
+    def __init__(self, backend, dist, hashes, ts_ns, seg_offset, hash_duration_ns, params, pairs=None, group=None):
+        self.backend, self.dist, self.group, self.params = backend, dist, group, params
+        self.world = dist.get_world_size(group) if dist is not None else 1
+        self.rank = dist.get_rank(group) if dist is not None else 0
+        self.hashes = np.ascontiguousarray(hashes, dtype=np.uint32)
+        self.ts_ns = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+        self.seg_offset = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        self.n_videos = (self.seg_offset.size - 1) // 2
+        self.hash_duration_ns = np.asarray(hash_duration_ns, dtype=np.uint64)
+        self.pairs = pair_list(self.n_videos) if pairs is None else \
+            np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self._all_pairs = np.array_equal(self.pairs, pair_list(self.n_videos))
+        seg_len = np.diff(self.seg_offset.astype(np.int64))
+        self.slices = shard_pairs(seg_len, self.pairs, self.world, bool(params.include_endings))
+        self.phase_s = {}
+
+    _tick = None   # set below: shared with SeasonJob
+
+    def run(self):
+        import time
+        t = time.perf_counter()
+        season = self.backend.upload_hashes(self.hashes, self.ts_ns, self.seg_offset)
+        t = self._tick("upload", t)
+        return search_tail(self, season, self.n_videos, t)
+
+
 class SeasonJob:
     """`needle search --analyze` for a library of videos across the ranks of a
     process group (or on one GPU when dist is None): the public multi-GPU call.
@@ -366,40 +440,7 @@ class SeasonJob:
             b.exchange(self.dist, ex, self.plan, self.seek_to_ns, self.group)
         season = b.season_from_gathered(ex, self.plan, self.world)
         t = self._tick("exchange_enqueue", t)
-        start, end = self.slices[self.rank]
-        if self.world > 1 and hasattr(b, "search_gathered"):
-            results = b.search_gathered(self.dist, season, self.params, self.pairs[start:end], start,
-                                        None if self._all_pairs else self.pairs, self.hash_duration_ns, self.slices,
-                                        self.group)
-            b.release(season)
-            self._tick("match+gather+vote", t)
-            return results
-        runs = globalize_runs(b.match(season, self.params, self.pairs[start:end]), start)
-        b.release(season)
-        t = self._tick("match", t)
-        all_runs = b.gather_runs(self.dist, runs, self.group) if self.world > 1 else runs
-        t = self._tick("gather_runs", t)
-        # the vote is per video and needs every run: all ranks have them, each votes for
-        # the videos v with v % world == rank, rank 0 collects the rows
-        n_videos = self.plan.n_videos
-        if self.world == 1:
-            table = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs)
-            self._tick("vote", t)
-            return results_rows_as_tuples(table)
-        mask = np.zeros(n_videos, np.uint8)
-        mask[self.rank::self.world] = 1
-        table = b.vote(self.hash_duration_ns, self.params, all_runs, self.pairs, video_mask=mask)
-        t = self._tick("vote", t)
-        cap = (n_videos + self.world - 1) // self.world
-        rows = b.gather_results(self.dist, table[self.rank::self.world], cap, self.group)
-        if self.rank != 0:
-            return None
-        full = np.zeros(n_videos, dtype=RESULT_DTYPE)
-        for r in range(self.world):
-            k = len(range(r, n_videos, self.world))
-            full[r::self.world] = rows[r, :k]
-        self._tick("gather_results", t)
-        return results_rows_as_tuples(full)
+        return search_tail(self, season, self.plan.n_videos, t)
 
     def run_host(self, local_segments):
         """From host PCM (pinned for full PCIe rate).  The copy is pipelined under K1
@@ -418,3 +459,6 @@ class SeasonJob:
         b.fingerprint_host_into(local_segments, self.plan, self.local_seek, ex)
         t = self._tick("upload+fingerprint", t)
         return self._after_fingerprint(ex, t)
+
+
+SearchJob._tick = SeasonJob._tick

@@ -66,6 +66,10 @@ class OracleBackend:
     def upload_pcm(self, segments):
         return list(segments)
 
+    def upload_hashes(self, hashes, ts_ns, seg_offset):
+        return synth.HashSeason(np.asarray(hashes, np.uint32), np.asarray(ts_ns, np.uint64),
+                                np.asarray(seg_offset, np.uint64), None)
+
     def alloc_exchange(self, plan):
         t = self.torch
         return {"hash_send": t.zeros(plan.cap, dtype=t.int32), "ts_send": t.zeros(plan.cap, dtype=t.int64),
@@ -218,3 +222,35 @@ def test_world2_gloo_equals_single_process_oracle(oracle, tmp_path, n_seasons, p
         want += res
     assert got == want
     assert sum(r[1] for r in got) >= len(got) - 1      # openings found
+
+
+def _search_worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        season = synth.make_hash_season(5, 260, 140, seed=7, run_len=120)
+        params = engine.match_params(include_endings=True)
+        job = nd.SearchJob(OracleBackend(), dist, season.hashes, season.ts_ns, season.seg_offset,
+                           season.hash_duration_ns, params)
+        assert job.slices[0][0] == 0 and job.slices[-1][1] == 10 and job.slices[0][1] == job.slices[1][0]
+        res = job.run()
+        if rank == 0:
+            np.save(out_path, np.array(res, dtype=np.uint64))
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_search_job_from_precomputed_hashes(oracle, tmp_path):
+    """BASELINE configs[3] in miniature: search-only from precomputed hashes, pairs sharded over 2 ranks."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_search_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = [tuple(int(x) for x in row) for row in np.load(out)]
+    season = synth.make_hash_season(5, 260, 140, seed=7, run_len=120)
+    st, want, _ = H.oracle_run(oracle, season, **H.params_kw(include_endings=True))
+    assert st == 0 and got == want
+    assert sum(r[1] for r in got) == 5

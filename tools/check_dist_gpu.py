@@ -79,7 +79,17 @@ def main():
             runs = hs.match(params, pairs=pairs).download()
             sub = engine.vote(hd, params, runs, pairs=pairs)
         assert a == sub and b == sub, (a, sub)
+    # search-only from precomputed hashes (BASELINE configs[3] in miniature): SearchJob
+    season = synth.make_hash_season(12, 900, 500, seed=3, run_len=200)
+    got = nd.SearchJob(backend, dist, season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns,
+                       params).run()
+    if rank == 0:
+        with engine.Context(local) as ctx:
+            assert got == ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
+        assert sum(r[1] for r in got) == 12
         print("DIST_OK %d" % world, flush=True)
+    else:
+        assert got is None
     dist.barrier()
     dist.destroy_process_group()
 
