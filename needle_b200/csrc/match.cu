@@ -609,6 +609,24 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
 // K4: simhash32 of both sides of every emitted run (comparator.rs:149-153,
 // 226-229): per-bit majority over hashes[i_end-len ..= i_end], ties -> 0.
 // One warp per run; lane b counts bit b.
+// 32 x 32 bit-matrix transpose across the warp (one row per lane, five exchange steps, the
+// recursive block swap of Hacker's Delight 7-3): afterwards lane l holds, one bit per source
+// lane, bit 31 - l of the words the lanes started with.
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+    uint32_t m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, x, j);
+        if ((lane & j) == 0) {
+            x ^= (x ^ (p >> j)) & m;
+        } else {
+            x ^= ((p ^ (x >> j)) & m) << j;
+        }
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
 __global__ void __launch_bounds__(128) simhash_kernel(const uint32_t *__restrict__ hashes,
                                                       const MatchProblem *__restrict__ problems,
                                                       DeviceRun *runs, const unsigned int *__restrict__ counters,
@@ -621,27 +639,26 @@ __global__ void __launch_bounds__(128) simhash_kernel(const uint32_t *__restrict
         const DeviceRun r = runs[w];
         const MatchProblem pr = problems[r.problem];
         const uint32_t count = r.len + 1;
-        uint32_t out[2];
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const uint32_t *h = hashes + (side == 0 ? pr.src_off + (r.i_end - r.len)
-                                                    : pr.dst_off + (r.j_end - r.len));
-            uint32_t ones = 0;
-            for (uint32_t base = 0; base < count; base += 32) {
-                uint32_t mine = (base + lane < count) ? h[base + lane] : 0u;
-                const uint32_t lim = min(32u, count - base);
-                for (uint32_t k = 0; k < lim; k++) {
-                    uint32_t v = __shfl_sync(0xffffffffu, mine, (int)k);
-                    ones += (v >> lane) & 1u;
-                }
-            }
-            // v[b] = ones - (count - ones) > 0
-            const bool bit = 2u * ones > count;
-            out[side] = __ballot_sync(0xffffffffu, bit);
+        const uint32_t *hs = hashes + pr.src_off + (r.i_end - r.len);
+        const uint32_t *hd = hashes + pr.dst_off + (r.j_end - r.len);
+        // Per 32 hashes of each side: one load per lane, a bit transpose (lane b then holds bit b of
+        // all 32), one POPC.  The next chunk is loaded before this one is reduced.
+        uint32_t ones_s = 0, ones_d = 0;
+        uint32_t ms = lane < count ? hs[lane] : 0u, md = lane < count ? hd[lane] : 0u;
+        for (uint32_t base = 0; base < count; base += 32) {
+            const uint32_t nxt = base + 32 + lane;
+            const uint32_t ns = nxt < count ? hs[nxt] : 0u, nd = nxt < count ? hd[nxt] : 0u;
+            ones_s += __popc(warp_bit_transpose(ms, lane));
+            ones_d += __popc(warp_bit_transpose(md, lane));
+            ms = ns;
+            md = nd;
         }
+        // v[b] = ones - (count - ones) > 0; lane l counted bit 31 - l
+        const uint32_t out_s = __brev(__ballot_sync(0xffffffffu, 2u * ones_s > count));
+        const uint32_t out_d = __brev(__ballot_sync(0xffffffffu, 2u * ones_d > count));
         if (lane == 0) {
-            runs[w].src_simhash = out[0];
-            runs[w].dst_simhash = out[1];
+            runs[w].src_simhash = out_s;
+            runs[w].dst_simhash = out_d;
         }
     }
 }

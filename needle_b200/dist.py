@@ -231,10 +231,12 @@ class GpuBackend:
     def exchange(self, dist, ex, plan: SeasonPlan, seek_to_ns, group=None):
         """ONE collective: the hashes.  Timestamps are a function of the index
         (analyzer.rs:309), so every rank fills in all of them itself."""
-        with self._on_stream():
-            dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
+        # the timestamps do not depend on anyone's hashes: filled first, while slower ranks are still
+        # fingerprinting, so that nothing but the match stands behind the collective
         self.ctx.timestamps_fill(ex["ts_recv"].data_ptr(), plan.dev_offset, plan.seg_len, seek_to_ns,
                                  stride=plan.stride)
+        with self._on_stream():
+            dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
 
     def season_from_gathered(self, ex, plan: SeasonPlan, world: int):
         h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])
