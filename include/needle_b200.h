@@ -421,6 +421,12 @@ int nb200_capi_frame_hashes_view(const struct FrameHashes *f, int ending, const 
                                  const uint64_t **ts_ns, uint64_t *n, uint64_t *hash_duration_ns,
                                  const char **md5);
 
+/* util::compute_header_md5sum (needle/src/util.rs:99-105): lower-case hex md5 of the first 8 KiB
+ * of a file, the key that ties a .needle.dat / .needle.skip.json to its video.  NB200_ERR_IO
+ * when the file is missing or shorter than 8 KiB (read_exact fails in the reference).
+ * Exported by libneedle.so. */
+int nb200_capi_header_md5(const char *path, char out[33]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "needle_audio_comparator_free": (None, [_P]),
     "needle_audio_comparator_run": (C.c_int, [_P, C.c_bool, C.c_bool, C.c_bool, C.c_bool, C.c_bool]),
     "nb200_capi_set_decoder": (C.c_int, [_P]),
+    "nb200_capi_header_md5": (C.c_int, [C.c_char_p, C.c_char_p]),
     "nb200_capi_frame_hashes_view": (C.c_int, [_P, C.c_int, _PP, _PP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                                C.POINTER(C.c_char_p)]),
 }

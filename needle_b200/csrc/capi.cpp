@@ -589,6 +589,14 @@ int nb200_capi_frame_hashes_view(const FrameHashes *f, int ending, const uint32_
     return NB200_OK;
 }
 
+int nb200_capi_header_md5(const char *path, char out[33]) {
+    if (!path || !out) return NB200_ERR_NULL_ARGUMENT;
+    std::string md5;
+    if (header_md5(path, &md5) != NeedleError_Ok) return NB200_ERR_IO;
+    memcpy(out, md5.c_str(), 33);
+    return NB200_OK;
+}
+
 const char *needle_error_to_str(enum NeedleError error) {
     switch (error) {   // needle-capi/src/lib.rs:139-203
     case NeedleError_Ok: return "No error";

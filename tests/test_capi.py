@@ -35,7 +35,8 @@ def test_exports_match_header():
     assert len(declared) == 13            # needle-capi/needle.h declares 13 functions
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True, check=True)
     exported = set(re.findall(r" T ((?:needle|nb200_capi)_[a-z0-9_]+)", out.stdout))
-    assert set(declared) | {"nb200_capi_set_decoder", "nb200_capi_frame_hashes_view"} == exported
+    assert set(declared) | {"nb200_capi_set_decoder", "nb200_capi_frame_hashes_view",
+                            "nb200_capi_header_md5"} == exported
     assert sorted(capi.PROTOTYPES) == sorted(exported)
 
 
@@ -101,6 +102,29 @@ def test_argument_conventions():
     assert L.needle_util_find_video_files(paths, 0, True, True, C.byref(vids), C.byref(n)) == capi.INVALID_ARGUMENT
     assert L.needle_util_find_video_files(paths, 2, True, True, C.byref(vids), C.byref(n)) == capi.UNKNOWN  # PathNotFound
     L.needle_util_video_files_free(None, 0)
+
+
+def test_header_md5_is_md5_of_the_first_8k(tmp_path):
+    """util::compute_header_md5sum (util.rs:99-105) against hashlib, incl. RFC 1321's padding edge
+    (8192 bytes = 128 full blocks + one padding block) and read_exact's failure on short files."""
+    L = capi.lib()
+    rng = np.random.default_rng(3)
+    out = C.create_string_buffer(33)
+    for size in (8192, 8193, 100_000):
+        p = tmp_path / ("f%d.bin" % size)
+        data = rng.integers(0, 256, size, dtype=np.uint8).tobytes()
+        p.write_bytes(data)
+        assert L.nb200_capi_header_md5(os.fsencode(str(p)), out) == 0
+        assert out.value.decode() == hashlib.md5(data[:8192]).hexdigest()
+    zeros = tmp_path / "zeros.bin"
+    zeros.write_bytes(bytes(8192))
+    assert L.nb200_capi_header_md5(os.fsencode(str(zeros)), out) == 0
+    assert out.value.decode() == hashlib.md5(bytes(8192)).hexdigest()
+    short = tmp_path / "short.bin"
+    short.write_bytes(b"x" * 8191)
+    assert L.nb200_capi_header_md5(os.fsencode(str(short)), out) != 0
+    assert L.nb200_capi_header_md5(os.fsencode(str(tmp_path / "missing")), out) != 0
+    assert L.nb200_capi_header_md5(None, out) != 0
 
 
 def write_wav(path, pcm, channels=1, rate=11025):
