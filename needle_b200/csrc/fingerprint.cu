@@ -584,6 +584,334 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
 }
 
 // ---------------------------------------------------------------------------
+// K1, tensor-memory variant ("tm"): the h32 kernel with the parked half of a frame in
+// TMEM instead of shared memory.  What capped h32 at 12 warps per SM was its 16.5 KB
+// exchange buffer per warp, and half of that buffer was only ever a lane-private parking
+// place (E[k] during pass 1, the odd rows of Z during the split).  Blackwell has 256 KB
+// of tensor memory per SM that this kernel's tensor-core-free arithmetic leaves idle:
+// tcgen05.st / tcgen05.ld (32x32b shape) move registers to and from a warp's own 32
+// TMEM lanes, i.e. exactly a lane-private spill space with its own data path:
+//
+//   pass 1, even rows -> 32-point FFT -> E[k]                      -> TMEM slot A
+//   pass 1, odd rows  -> 32-point FFT -> O[k];  E[k] <- slot A
+//                        Y[k+32] = E - W64^k O -> row k of the exchange buffer
+//                        Y[k]    = E + W64^k O -> slot A (over E)
+//   pass 2, q = 1: rows (transposed) -> twiddle -> 32-point FFT -> Z odd -> TMEM slot B
+//   Y[k] <- slot A -> rows;  pass 2, q = 0 -> Z even, stays in registers
+//   split: Z odd <- slot B four values at a time; the partner lane's values by shuffle
+//
+// The exchange buffer shrinks to 32 rows (8.25 KB per warp, still the PCM landing zone of
+// the bulk copy), so 16 warps fit (4 per scheduler, 128 registers each); shared-memory
+// traffic drops by the park/unpark stores and loads (~250 of ~930 wavefronts per frame).
+// TMEM: 2 slots x 64 columns per warp, 4 warps per lane quadrant -> all 512 columns.
+constexpr int TM_ROWS = 32;
+constexpr int TM_WARP_BYTES = TM_ROWS * XCHG_STRIDE * 8;     // 8,448 B
+static_assert(PCM_COPY_BYTES <= TM_WARP_BYTES, "PCM must fit the exchange buffer");
+template <int NW> constexpr int tm_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * TM_WARP_BYTES + NW * 8 + 16; }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 8 complex values = 16 columns of this warp's lanes
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, f2 a0, f2 a1, f2 a2, f2 a3, f2 a4, f2 a5, f2 a6, f2 a7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(a0.x), "f"(a0.y), "f"(a1.x), "f"(a1.y), "f"(a2.x), "f"(a2.y), "f"(a3.x), "f"(a3.y),
+                   "f"(a4.x), "f"(a4.y), "f"(a5.x), "f"(a5.y), "f"(a6.x), "f"(a6.y), "f"(a7.x), "f"(a7.y) : "memory");
+}
+// The load is asynchronous: its registers are valid after tcgen05.wait::ld.  The wait takes the
+// registers as read-write operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, f2 (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y),
+                   "=f"(r[4].x), "=f"(r[4].y), "=f"(r[5].x), "=f"(r[5].y), "=f"(r[6].x), "=f"(r[6].y), "=f"(r[7].x), "=f"(r[7].y)
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(f2 (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0].x), "+f"(r[0].y), "+f"(r[1].x), "+f"(r[1].y), "+f"(r[2].x), "+f"(r[2].y), "+f"(r[3].x), "+f"(r[3].y),
+                   "+f"(r[4].x), "+f"(r[4].y), "+f"(r[5].x), "+f"(r[5].y), "+f"(r[6].x), "+f"(r[6].y), "+f"(r[7].x), "+f"(r[7].y)
+                 :: "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, f2 (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y)
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld4x2(f2 (&r)[4], f2 (&q)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0].x), "+f"(r[0].y), "+f"(r[1].x), "+f"(r[1].y), "+f"(r[2].x), "+f"(r[2].y), "+f"(r[3].x), "+f"(r[3].y),
+                   "+f"(q[0].x), "+f"(q[0].y), "+f"(q[1].x), "+f"(q[1].y), "+f"(q[2].x), "+f"(q[2].y), "+f"(q[3].x), "+f"(q[3].y)
+                 :: "memory");
+}
+__device__ __forceinline__ f2 tmem_ld1_wait(uint32_t taddr) {
+    f2 r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=f"(r.x), "=f"(r.y) : "r"(taddr) : "memory");
+    return r;
+}
+
+// split + power + chroma fold of bin k = L + 32 t (t is a compile-time constant after unrolling):
+// z = Z[k], zp = Z[2048 - k]
+__device__ __forceinline__ void tm_bin(const int t, const f2 z, const f2 zp, const f2 lw, const uint32_t (&fold_m)[4],
+                                       float (&acc)[FP_BANDS]) {
+    // 2E = (a+c, b-d), 2O = (b+d, c-a) with Z[k] = a+ib, Z[N-k] = c+id
+    const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+    const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+    const f2 w = cmulc(lw, c_w128[t], c_w128r[t]);   // W_4096^(L + 32 t)
+    const f2 x = add2(e, cmul3(o, w));               // 2 X[k]
+    const float pw = x.x * x.x + x.y * x.y;          // 4 |X[k]|^2
+#define FOLDC(T, NOTE, IDX, LANES)                                                   \
+    if (t == T) {                                                                    \
+        if ((LANES) == 0xffffffffu) acc[NOTE] += pw;                                 \
+        else if (fold_m[(IDX) >> 5] & (1u << ((IDX) & 31))) acc[NOTE] += pw;         \
+    }
+#include "fp_chroma_fold.inc"
+#undef FOLDC
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Args a) {
+    static_assert(NW % 4 == 0 && NW <= 16, "4 warps per TMEM lane quadrant, 128 columns each");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    f2 *s_window = reinterpret_cast<f2 *>(smem_raw);                     // 1024: first half of the window
+    f2 *s_twiddle = s_window + FP_HALF / 2;                              // 2048
+    unsigned char *s_warp = reinterpret_cast<unsigned char *>(s_twiddle + FP_HALF);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_warp + NW * TM_WARP_BYTES);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + NW);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
+        if (i < FP_HALF / 2) s_window[i] = a.window[i];
+        s_twiddle[i] = a.twiddle[i];
+    }
+    if (threadIdx.x < NW) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t TM_COLS = 512;                                    // power of two >= NW / 4 * 128
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), TM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    // this warp's lanes (its quadrant of the 128) and its two 64-column slots
+    const uint32_t tA = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 128u;
+    const uint32_t tB = tA + 64u;
+
+    f2 *xchg = reinterpret_cast<f2 *>(s_warp + warp * TM_WARP_BYTES);
+    const uint32_t *pcm_words = reinterpret_cast<const uint32_t *>(xchg);
+    const uint32_t bar = smem_u32(s_bar + warp);
+    const uint32_t xchg_addr = smem_u32(xchg);
+    const uint32_t lane_addr = xchg_addr + 8u * (uint32_t)lane;                 // &xchg[0 * STRIDE + lane]
+    constexpr uint32_t ROW = XCHG_STRIDE * 8u;                                  // bytes per row
+    const int partner = (32 - lane) & 31;
+    const f2 lane_w = a.lane_w[lane];
+
+    // chroma fold: bit idx of fold_m[] says whether this lane's bin of that (row, pitch class) entry
+    // belongs to the class (fp_chroma_fold.inc, FOLDC).  Four registers for the whole kernel; the
+    // range compares they replace were ~300 instructions per frame.
+    uint32_t fold_m[4] = {0u, 0u, 0u, 0u};
+#define FOLDC(T, NOTE, IDX, LANES) \
+    if (((LANES) >> lane) & 1u) fold_m[(IDX) >> 5] |= 1u << ((IDX) & 31);
+#include "fp_chroma_fold.inc"
+#undef FOLDC
+    asm volatile("" : "+r"(fold_m[0]), "+r"(fold_m[1]), "+r"(fold_m[2]), "+r"(fold_m[3]));
+
+    const uint32_t n_blocks = (a.frame_end - a.frame_begin + NW - 1) / NW;
+    uint32_t blk = blockIdx.x;
+    uint32_t frame = a.frame_begin + blk * NW + warp;
+    uint32_t phase = 0;
+    uint32_t delta = 0;
+    if (blk < n_blocks && frame < a.frame_end) {
+        const int16_t *src = frame_src(a, frame);
+        delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        if (lane == 0) {
+            mbar_expect_tx(bar, PCM_COPY_BYTES);
+            bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+        }
+    }
+
+    for (; blk < n_blocks; blk += gridDim.x) {
+        frame = a.frame_begin + blk * NW + warp;
+        if (frame >= a.frame_end) break;   // warp-uniform; only warp-level sync below
+
+        f2 v[32];
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        const uint32_t *p = pcm_words + (delta >> 2) + lane;
+        const uint32_t shift = (delta & 2) * 8;
+        // ---- pass 1: even rows (half = 0), then odd rows (half = 1); one copy of the code
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            const uint32_t *ph = p + 32 * half;
+            const f2 *wlo = s_window + 32 * half + lane;
+            const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                const f2 s = s16x2_to_float(__funnelshift_r(w0, w1, shift));
+                const f2 wv = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                v[j] = mul2(s, wv);
+            }
+            if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
+            fft32(v);
+            if (half == 0) {
+                // E[k] sits in v[pos32(k)]; parked in register order (slot j = v[j])
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    tmem_st8(tA + 16 * c, v[8 * c], v[8 * c + 1], v[8 * c + 2], v[8 * c + 3], v[8 * c + 4],
+                             v[8 * c + 5], v[8 * c + 6], v[8 * c + 7]);
+            } else {
+                tmem_wait_st();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    f2 e[8];
+                    tmem_ld8(tA + 16 * c, e);
+                    tmem_wait_ld8(e);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int k = c + 4 * i;   // pos32(k) = 8 c + i
+                        const f2 o = k == 0 ? v[8 * c + i] : cmulc(v[8 * c + i], c_w64[k], c_w64r[k]);
+                        sts2(lane_addr + k * ROW, sub2(e[i], o));   // Y[k + 32] -> row k
+                        e[i] = add2(e[i], o);                       // Y[k]      -> back to slot A
+                    }
+                    tmem_st8(tA + 16 * c, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: k1 = L + 32 (q = 1: odd t, parked in slot B), then k1 = L (q = 0: even t, in registers)
+#pragma unroll 1
+        for (int q = 1; q >= 0; q--) {
+            if (q == 0) {
+                // Y[k], k < 32, from slot A into the rows that pass q = 1 has consumed
+                tmem_wait_st();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    f2 y[8];
+                    tmem_ld8(tA + 16 * c, y);
+                    tmem_wait_ld8(y);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sts2(lane_addr + (c + 4 * i) * ROW, y[i]);
+                }
+                __syncwarp();
+            }
+            const f2 *row = xchg + lane * XCHG_STRIDE;
+            const f2 *tw = s_twiddle + lane + 32 * q;
+#pragma unroll
+            for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul3(row[n2], tw[n2 * 64]);
+            __syncwarp();   // the rows are consumed
+            if (q == 0) {
+                // the buffer is free: start the next frame's PCM on its way
+                const uint32_t nblk = blk + gridDim.x;
+                const uint32_t nframe = a.frame_begin + nblk * NW + warp;
+                if (nblk < n_blocks && nframe < a.frame_end) {
+                    const int16_t *src = frame_src(a, nframe);
+                    delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+                    fence_proxy_async();
+                    if (lane == 0) {
+                        mbar_expect_tx(bar, PCM_COPY_BYTES);
+                        bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+                    }
+                }
+            }
+            fft32(v);
+            if (q == 1) {
+                // Z[L + 32 (2 k2 + 1)] parked in k2 order: slot B column 2 k2
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                    tmem_st8(tB + 16 * c, v[pos32(8 * c)], v[pos32(8 * c + 1)], v[pos32(8 * c + 2)], v[pos32(8 * c + 3)],
+                             v[pos32(8 * c + 4)], v[pos32(8 * c + 5)], v[pos32(8 * c + 6)], v[pos32(8 * c + 7)]);
+            }
+        }
+        tmem_wait_st();
+        // Z[L + 32 t]: t even -> v[pos32(t / 2)], t odd -> slot B entry (t - 1) / 2
+
+        float acc[FP_BANDS];
+#pragma unroll
+        for (int b = 0; b < FP_BANDS; b++) acc[b] = 0.f;
+        f2 lw = lane_w;
+        asm volatile("" : "+f"(lw.x), "+f"(lw.y));   // keep W_4096^(L + 32 t) from being hoisted (41 spilled values)
+        // rows t = 2 a and t = 2 a + 1 together: both need the parked entry 31 - a (the even row's
+        // partner value is the partner lane's entry; lane 0's partner of the odd row is its own)
+#pragma unroll
+        for (int g = 0; g < 5; g++) {
+            f2 pa[4], pb[4];
+            tmem_ld4(tB + 2 * (4 * g), pa);          // entries 4 g .. 4 g + 3
+            tmem_ld4(tB + 2 * (28 - 4 * g), pb);     // entries 28 - 4 g .. 31 - 4 g: pb[3 - i] = entry 31 - (4 g + i)
+            tmem_wait_ld4x2(pa, pb);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int a2 = 4 * g + i;
+                {   // t = 2 a: own register; partner's parked entry 31 - a
+                    const f2 z = v[pos32(a2)];
+                    f2 zp;
+                    zp.x = __shfl_sync(0xffffffffu, pb[3 - i].x, partner);
+                    zp.y = __shfl_sync(0xffffffffu, pb[3 - i].y, partner);
+                    const f2 own = v[pos32(a2 == 0 ? 0 : 32 - a2)];   // lane 0: k = 32 t pairs with 32 (64 - t), even
+                    if (lane == 0) zp = own;
+                    tm_bin(2 * a2, z, zp, lw, fold_m, acc);
+                }
+                {   // t = 2 a + 1: own parked entry a; partner's register; lane 0: its own parked entry 31 - a
+                    const f2 z = pa[i];
+                    const f2 ps = v[pos32(31 - a2)];
+                    f2 zp;
+                    zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
+                    zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
+                    if (lane == 0) zp = pb[3 - i];
+                    tm_bin(2 * a2 + 1, z, zp, lw, fold_m, acc);
+                }
+            }
+        }
+        {   // t = 40: partner's parked entry 11
+            const f2 p11 = tmem_ld1_wait(tB + 2 * 11);
+            const f2 z = v[pos32(20)];
+            f2 zp;
+            zp.x = __shfl_sync(0xffffffffu, p11.x, partner);
+            zp.y = __shfl_sync(0xffffffffu, p11.y, partner);
+            const f2 own = v[pos32(12)];
+            if (lane == 0) zp = own;
+            tm_bin(40, z, zp, lw, fold_m, acc);
+        }
+        // 12 sums over 32 lanes with halving butterflies (as in the h32 kernel): 18 shuffles
+        float r6[6], r3[3];
+        {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const float keep = up ? acc[i + 6] : acc[i], send = up ? acc[i] : acc[i + 6];
+                r6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float keep = up ? r6[i + 3] : r6[i], send = up ? r6[i] : r6[i + 3];
+                r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) r3[i] += __shfl_xor_sync(0xffffffffu, r3[i], o);
+        }
+        if ((lane & 7) == 0) {
+            float *out = a.chroma + (uint64_t)frame * FP_BANDS + 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1);
+            out[0] = 0.25f * r3[0];
+            out[1] = 0.25f * r3[1];
+            out[2] = 0.25f * r3[2];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
+}
+
+// ---------------------------------------------------------------------------
 // K1, four-warps-per-frame variant ("g4").  The warp-per-frame kernel above keeps
 // 64 complex values per lane: 255 registers, 8 warps per SM, and ptxas has no
 // room to overlap dependent packed ops (ncu: issue active 49 %, stall "wait" 1.0).
@@ -1072,6 +1400,10 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
                                  h32_smem_bytes<10>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  h32_smem_bytes<8>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<16>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<12>()));
     ctx->fp_ready = true;
     return NB200_OK;
 }
@@ -1190,8 +1522,18 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
             const uint32_t nf = f1 - f0;
-            const int variant = ctx->k1_variant == 0 ? 12 : ctx->k1_variant;   // default: h32, 12 warps per SM
-            if (variant >= 8) {
+            const int variant = ctx->k1_variant == 0 ? 16 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM
+            if (variant >= 16) {
+                // tensor-memory kernel: 16 (or, variant 112, 12) warps per SM
+                k1.frame_begin = f0;
+                k1.frame_end = f1;
+                const uint32_t nw = variant == 112 ? 12u : 16u;
+                const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
+                if (nw == 16)
+                    fp_fft_chroma_tm_kernel<16><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                else
+                    fp_fft_chroma_tm_kernel<12><<<grid1, 12 * 32, tm_smem_bytes<12>(), st>>>(k1);
+            } else if (variant >= 8) {
                 k1.frame_begin = f0;
                 k1.frame_end = f1;
                 const uint32_t nw = (uint32_t)variant;
