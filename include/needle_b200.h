@@ -51,6 +51,7 @@ enum {
     NB200_ERR_FORMAT = 8,            /* NeedleError_InvalidFrameHashData / InvalidVersion */
     NB200_ERR_STATE = 9,             /* call order violated (e.g. feed before start) */
     NB200_ERR_COMPARATOR_MINIMUM_PATHS = 10, /* NeedleError_ComparatorMinimumPaths */
+    NB200_ERR_NCCL = 11,             /* NCCL missing (dlopen) or a collective failed; see nb200_last_error */
 };
 const char *nb200_status_str(int status);
 /* Last CUDA error text seen by this thread ("" if none). */
@@ -278,6 +279,13 @@ uint64_t nb200_num_raw_hashes(uint64_t n_mono_samples);
 int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_t *n_samples_total,
                         int channels, uint32_t n_segments, nb200_pcmset **out);
 void nb200_pcmset_free(nb200_pcmset *ps);
+/* A PCM set over mono S16 @ 11025 Hz that is ALREADY in device memory (decoded or generated on the
+ * GPU, or placed there by the caller's own copies): nothing is copied, the arrays stay the
+ * caller's.  d_pcm 16-byte aligned; dev_offset[s] = element offset of segment s (any value);
+ * capacity = elements allocated at d_pcm, at least 8 beyond the end of every segment (the frame
+ * loads are 16-byte bulk copies).  Segments come in (opening, ending) pairs like everywhere else. */
+int nb200_pcmset_view(nb200_ctx *ctx, const void *d_pcm, const uint64_t *dev_offset, const uint64_t *n_mono_samples,
+                      uint32_t n_segments, uint64_t capacity, nb200_pcmset **out);
 
 /* Fingerprint every segment on the GPU and keep raw index 0, stride, 2*stride..
  * (step_by, analyzer.rs:293-305), stamped
@@ -378,6 +386,71 @@ int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, u
                       const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                       uint64_t n_pairs, const nb200_match_params *params, int do_vote,
                       nb200_search_result *results, uint64_t *max_found);
+
+/* ------------------------------------------------ multi-GPU jobs (one box)
+ *
+ * The reference fans out over videos and over pairs inside ONE process with rayon
+ * (Analyzer::run, analyzer.rs:437-445; Comparator::run_with_frame_hashes,
+ * comparator.rs:549-564).  These calls are that fan-out across the GPUs of a box:
+ * videos are sharded for fingerprinting, the hash arrays are all-gathered once
+ * (NCCL, loaded with dlopen: no link-time dependency), the pair list is sharded by
+ * table cells for matching, every rank's runs are pushed into rank 0's memory over
+ * NVLink (peer stores from a kernel, not a collective) and rank 0 votes.
+ *
+ * nb200_comm = one rank: a context plus its NCCL communicator.  Two ways to get them:
+ *   - one process, N devices (needle's own shape): nb200_comm_init_all over N contexts
+ *     (ncclCommInitAll); pass all N comms to the job calls;
+ *   - one process per device (torchrun, MPI): rank 0 calls nb200_comm_unique_id, the host
+ *     framework hands the 128 bytes to every process, each calls nb200_comm_init_rank and
+ *     passes its one comm to the job calls.
+ * Job calls are collective: every rank makes the same calls in the same order with the same
+ * global metadata; per-video results land in `results` of the process that drives rank 0.
+ * A comm switches its context to NB200_OPT_DEFER_WAIT. */
+typedef struct nb200_comm nb200_comm;
+typedef struct nb200_mjob nb200_mjob;
+#define NB200_UNIQUE_ID_BYTES 128
+int nb200_comm_unique_id(uint8_t id[NB200_UNIQUE_ID_BYTES]);
+int nb200_comm_init_rank(nb200_ctx *ctx, const uint8_t id[NB200_UNIQUE_ID_BYTES], int rank, int world,
+                         nb200_comm **out);
+int nb200_comm_init_all(nb200_ctx *const *ctxs, int n, nb200_comm **out /* [n] */);
+int nb200_comm_info(const nb200_comm *comm, int *rank, int *world);
+void nb200_comm_destroy(nb200_comm *comm);
+
+/* `needle search` from precomputed frame hashes (.needle.dat) across the ranks: every rank is
+ * given the same season (KB..MB, uploaded once, resident for the life of the job) and matches its
+ * slice of the pair list.  comms[n_local] = the ranks this process drives, ascending.
+ * Replaces the pair loop of Comparator::run_with_frame_hashes (comparator.rs:532-578). */
+int nb200_mjob_search_create(nb200_comm *const *comms, int n_local, const uint32_t *hashes, const uint64_t *ts_ns,
+                             const uint64_t *seg_offset, uint32_t n_videos, const uint64_t *hash_duration_ns,
+                             const uint32_t (*pairs)[2], uint64_t n_pairs, const nb200_match_params *params,
+                             nb200_mjob **out);
+/* `needle search --analyze` for a library of videos: n_mono_samples / seek_to_ns [2 * n_videos]
+ * describe ALL segments (opening_k, ending_k); the library decides which rank fingerprints which
+ * video (nb200_mjob_video_rank) and each process supplies PCM only for its own ranks' videos.
+ * Replaces Analyzer::run's per-video loop (analyzer.rs:437-445) + the pair loop. */
+int nb200_mjob_season_create(nb200_comm *const *comms, int n_local, const uint64_t *n_mono_samples,
+                             const uint64_t *seek_to_ns, uint32_t n_videos, uint64_t hash_duration_ns,
+                             const uint32_t (*pairs)[2], uint64_t n_pairs, const nb200_match_params *params,
+                             nb200_mjob **out);
+int nb200_mjob_video_rank(const nb200_mjob *job, uint32_t *rank_of_video /* [n_videos] */);
+/* Season job: mono PCM of this process's videos into HBM, for nb200_mjob_run(job, NULL, ..).
+ * pcm[2 * n_videos], entries of videos that belong to other processes' ranks are ignored. */
+int nb200_mjob_upload_pcm(nb200_mjob *job, const int16_t *const *pcm);
+/* One pass of the job.  Season job: host_pcm != NULL streams the PCM from (pinned) host memory
+ * underneath K1, NULL uses the uploaded PCM.  Search job: host_pcm is ignored.
+ * results[n_videos]: required where rank 0 is local. */
+int nb200_mjob_run(nb200_mjob *job, const int16_t *const *host_pcm, nb200_search_result *results);
+/* CUDA-event milliseconds of the phases of the last run on this process's lowest rank. */
+enum {
+    NB200_MJOB_FINGERPRINT = 0,   /* K1 + K2 (+ pipelined H2D) */
+    NB200_MJOB_HASH_ALLGATHER = 1,/* ncclAllGather of the hashes (includes waiting for the slowest rank) */
+    NB200_MJOB_MATCH = 2,         /* K3 + K4 on this rank's slice of the pair list */
+    NB200_MJOB_RUN_PUSH_WAIT = 3, /* rank 0: until every rank's run block has landed */
+    NB200_MJOB_VOTE = 4,          /* rank 0: heap replay + find_best_match + results to the host */
+    NB200_MJOB_PHASES = 5
+};
+int nb200_mjob_phase_ms(const nb200_mjob *job, float *ms /* [NB200_MJOB_PHASES] */);
+void nb200_mjob_free(nb200_mjob *job);
 
 /* ------------------------------------------------------------ persistence */
 

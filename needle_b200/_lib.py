@@ -24,6 +24,7 @@ ERR_IO = 7
 ERR_FORMAT = 8
 ERR_STATE = 9
 ERR_COMPARATOR_MINIMUM_PATHS = 10
+ERR_NCCL = 11
 OPT_FORCE_GENERAL_MATCH = 1
 OPT_K1_VARIANT = 2
 OPT_MATCH_DENSE = 3
@@ -119,6 +120,7 @@ PROTOTYPES = {
     "nb200_num_raw_hashes": (C.c_uint64, [C.c_uint64]),
     "nb200_pcmset_upload": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, _PP]),
     "nb200_pcmset_free": (None, [_P]),
+    "nb200_pcmset_view": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint64, _PP]),
     "nb200_fingerprint_run": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _PP]),
     "nb200_fingerprint_layout": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _U64P]),
     "nb200_fingerprint_run_into": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, C.c_uint64, _P, _P, _P, C.c_uint64]),
@@ -141,6 +143,20 @@ PROTOTYPES = {
     "nb200_match_export": (C.c_int, [_P, _P, _P, C.c_uint64, C.POINTER(MatchParams), C.c_uint32, _P, C.c_uint64]),
     "nb200_vote_blocks": (C.c_int, [_P, _P, C.c_uint32, C.c_uint64, _P, C.c_uint32, _P, C.c_uint64,
                                     C.POINTER(MatchParams), C.c_int, C.POINTER(SearchResultC), _U64P]),
+    "nb200_comm_unique_id": (C.c_int, [_P]),
+    "nb200_comm_init_rank": (C.c_int, [_P, _P, C.c_int, C.c_int, _PP]),
+    "nb200_comm_init_all": (C.c_int, [_P, C.c_int, _P]),
+    "nb200_comm_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nb200_comm_destroy": (None, [_P]),
+    "nb200_mjob_search_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_uint32, _P, _P, C.c_uint64,
+                                           C.POINTER(MatchParams), _PP]),
+    "nb200_mjob_season_create": (C.c_int, [_P, C.c_int, _P, _P, C.c_uint32, C.c_uint64, _P, C.c_uint64,
+                                           C.POINTER(MatchParams), _PP]),
+    "nb200_mjob_video_rank": (C.c_int, [_P, _P]),
+    "nb200_mjob_upload_pcm": (C.c_int, [_P, _P]),
+    "nb200_mjob_run": (C.c_int, [_P, _P, C.POINTER(SearchResultC)]),
+    "nb200_mjob_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "nb200_mjob_free": (None, [_P]),
     "nb200_framehashes_write": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, _P, _P, C.c_uint64,
                                           C.c_uint64, C.c_char_p]),
     "nb200_framehashes_read": (C.c_int, [C.c_char_p, _PP, _PP, _U64P, _PP, _PP, _U64P, _U64P,
@@ -170,7 +186,7 @@ def lib():
 
 def check(status: int, where: str):
     if status != OK:
-        detail = lib().nb200_last_error().decode() if status == ERR_CUDA else ""
+        detail = lib().nb200_last_error().decode() if status in (ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_TOO_LARGE) else ""
         raise Nb200Error(status, where, detail)
 
 

@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libneedle_b200.so")
 CAPI_LIB = os.path.join(HERE, "libneedle.so")   # the needle-capi ABI (include/needle.h) over libneedle_b200.so
 OBJ_DIR = os.path.join(HERE, "_obj")
 
-SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote_device.cu", "vote.cpp", "persist.cpp"]
+SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote_device.cu", "multi.cu", "vote.cpp", "persist.cpp"]
 HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"),
            os.path.join(INCLUDE, "needle_b200.h"), os.path.join(INCLUDE, "needle.h")]
 

@@ -117,6 +117,7 @@ const char *nb200_status_str(int status) {
     case NB200_ERR_FORMAT: return "invalid frame hash data";
     case NB200_ERR_STATE: return "call order violated";
     case NB200_ERR_COMPARATOR_MINIMUM_PATHS: return "comparator needs at least two videos";
+    case NB200_ERR_NCCL: return "NCCL error (library not found, or a collective failed; see nb200_last_error)";
     default: return "unknown status";
     }
 }
@@ -203,7 +204,7 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
         return NB200_OK;
     case NB200_OPT_K1_VARIANT:
         if (value != 0 && value != 1 && (value < 4 || value > 6) && value != 8 && value != 10 && value != 12 &&
-            value != 16 && value != 112)
+            value != 16 && value != 17 && value != 112)
             return NB200_ERR_INVALID_ARGUMENT;
         ctx->k1_variant = (int)value;
         return NB200_OK;

@@ -120,6 +120,11 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     DevBuf() = default;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), pool(std::move(o.pool)), borrowed(o.borrowed) {
+        o.p = nullptr;
+        o.bytes = 0;
+        o.borrowed = false;
+    }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
@@ -181,7 +186,7 @@ struct nb200_ctx {
     nb200::DevBuf d_tsfill;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
-    nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes;
+    nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes, d_fp_wsplit;
     nb200::DevBuf d_g4_twa, d_g4_twb, d_g4_base, d_g4_notes;
     int k1_variant = 0;   // 0: default (= 16); 1: 64 values per lane; 8/10/12: 32 values per lane, half parked in shared memory; 16 (112): half parked in TMEM, 16 (12) warps
                           // per SM; 4/5/6: four warps per frame, that many frames per CTA
@@ -242,6 +247,15 @@ struct DeviceRun {   // 64 bytes
 };
 static_assert(sizeof(DeviceRun) == 64, "DeviceRun is exchanged between ranks as raw bytes");
 
+// A rank's match output as one message: this 64-byte header, then DeviceRun records (vote_device.cu, multi.cu)
+struct RunBlockHeader {
+    uint32_t n_found;    // runs the match found
+    uint32_t n_stored;   // min(n_found, capacity): the records that follow
+    uint32_t flags;      // bit 0: a Duration subtraction would have underflowed
+    uint32_t reserved[13];
+};
+static_assert(sizeof(RunBlockHeader) == 64, "header and records share one 64-byte grid");
+
 // What match_enqueue left on ctx's stream and in ctx's scratch (d_runs, d_counters):
 // nothing has been waited for.  counters[1] = number of runs found (may exceed
 // run_cap: then only run_cap were stored and the caller re-runs with more room),
@@ -272,6 +286,11 @@ constexpr uint32_t VOTE_FLAG_FALLBACK = 2u;    // a table or a video exceeds the
 int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_n_runs, uint32_t run_cap,
                  const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                  uint64_t n_pairs, const nb200_match_params *params);
+
+int vote_blocks_impl(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes, uint64_t cap,
+                     const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                     uint64_t n_pairs, const nb200_match_params *params, int do_vote,
+                     nb200_search_result *results, uint64_t *max_found);
 
 // vote.cpp ---------------------------------------------------------------
 void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order

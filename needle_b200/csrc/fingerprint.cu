@@ -167,6 +167,12 @@ __device__ __forceinline__ f2 s16x2_to_float(uint32_t w) {
     return add2(biased, make_float2(-8421376.0f, -8421376.0f));
 }
 
+// the same through the conversion unit: two I2F.S16 (one per half of the word) on the XU pipe,
+// which nothing else in K1 uses -- no bias trick, no work for the FMA pipe
+__device__ __forceinline__ f2 s16x2_to_float_xu(uint32_t w) {
+    return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+}
+
 // ---- 1-D bulk async copy (TMA) + mbarrier, shared::cta addresses as u32
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -217,6 +223,7 @@ struct K1Args {
     const float2 *window;    // [2048]  (w[2n], w[2n+1]) / 32767
     const float2 *twiddle;   // [32][64] W_2048^(n2 k1)
     const float2 *lane_w;    // [32] W_4096^L
+    const float2 *wsplit;    // [41][32] W_4096^(L + 32 t)
     float *chroma;           // [total_frames][12]
 };
 
@@ -607,7 +614,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
 constexpr int TM_ROWS = 32;
 constexpr int TM_WARP_BYTES = TM_ROWS * XCHG_STRIDE * 8;     // 8,448 B
 static_assert(PCM_COPY_BYTES <= TM_WARP_BYTES, "PCM must fit the exchange buffer");
-template <int NW> constexpr int tm_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * TM_WARP_BYTES + NW * 8 + 16; }
+template <int NW> constexpr int tm_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * TM_WARP_BYTES + NW * 8 + 16 + FP_T * 32 * 8; }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -655,6 +662,110 @@ __device__ __forceinline__ f2 tmem_ld1_wait(uint32_t taddr) {
     return r;
 }
 
+// ---- revision 2 of the arithmetic: fewer FMA-pipe cycles for the same transform.
+// On sm_100a a packed FFMA2/FADD2/FMUL2 holds a scheduler's FMA pipe for two cycles and a
+// scalar FFMA for one, so what counts is the number of scalar-equivalent results.  Two things
+// waste them in the (re, im)-packed form: a complex product by a run-time twiddle (three packed
+// ops = 6 cycles for 4 useful multiply-adds), and a product followed by a radix-2 butterfly
+// (a + w b, a - w b) computed as product, sum, difference (8 cycles packed).  Here
+//   * the sum is accumulated INTO the product (two FFMA2 on top of `a`) and the difference is
+//     2 a - (a + w b): 6 cycles, three instructions;
+//   * products by shared-memory twiddles are four scalar FFMA (4 cycles), also accumulated.
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+// (plus, minus) = (a + w b, a - w b); wr = (-w.y, w.x)
+__device__ __forceinline__ void bfly_w(const f2 a, const f2 b, const f2 w, const f2 wr, f2 &plus, f2 &minus) {
+    plus = fma2(by(b), wr, fma2(bx(b), w, a));
+    minus = fma2(a, make_float2(2.f, 2.f), neg2(plus));
+}
+// a * w and c + a * w with scalar FFMA (run-time w: no rotated copy needed)
+__device__ __forceinline__ f2 cmul_s(const f2 a, const f2 w) {
+    f2 r;
+    r.x = __fmaf_rn(-a.y, w.y, __fmul_rn(a.x, w.x));
+    r.y = __fmaf_rn(a.y, w.x, __fmul_rn(a.x, w.y));
+    return r;
+}
+__device__ __forceinline__ f2 cmad_s(const f2 a, const f2 w, const f2 c) {
+    f2 r;
+    r.x = __fmaf_rn(-a.y, w.y, __fmaf_rn(a.x, w.x, c.x));
+    r.y = __fmaf_rn(a.y, w.x, __fmaf_rn(a.x, w.y, c.y));
+    return r;
+}
+// second half of fft8: v[0..3S] = b0..b3 (sums), v[4S] = b4, v[5S] = t5, v[6S] = e6, v[7S] = t7 (differences)
+template <int S> __device__ __forceinline__ void fft8_tail(f2 *v) {
+    constexpr float R = 0.70710678118654752440f;
+    const f2 b0 = v[0], b1 = v[S], b2 = v[2 * S], b3 = v[3 * S];
+    const f2 b4 = v[4 * S], t5 = v[5 * S], e6 = v[6 * S], t7 = v[7 * S];
+    const f2 b5 = fma2(by(t5), make_float2(R, R), mul2(bx(t5), make_float2(R, -R)));
+    const f2 b7 = fma2(by(t7), make_float2(R, -R), mul2(bx(t7), make_float2(-R, -R)));
+    {
+        const f2 d0 = add2(b0, b2), d1 = sub2(b0, b2), d2 = add2(b1, b3), e = sub2(b1, b3);
+        v[0] = add2(d0, d2);
+        v[2 * S] = add_mi(d1, e);
+        v[4 * S] = sub2(d0, d2);
+        v[6 * S] = sub_mi(d1, e);
+    }
+    {
+        const f2 d0 = add_mi(b4, e6), d1 = sub_mi(b4, e6), d2 = add2(b5, b7), e = sub2(b5, b7);
+        v[S] = add2(d0, d2);
+        v[3 * S] = add_mi(d1, e);
+        v[5 * S] = sub2(d0, d2);
+        v[7 * S] = sub_mi(d1, e);
+    }
+}
+// fft32 whose first radix-2 layer the caller has already done (fused with the window or the
+// twiddles): for every n1 < 8, with c_i = x[n1 + 8 i]:
+//   v[n1] = c0 + c2, v[n1 + 16] = c0 - c2, v[n1 + 8] = c1 + c3, v[n1 + 24] = c1 - c3.
+// Output order as fft32(): X[4 k1 + k2] at v[k1 + 8 k2].
+__device__ __forceinline__ void fft32_tail(f2 *v) {
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) {
+        const f2 d0 = v[n1], d2 = v[n1 + 8], d1 = v[n1 + 16], e = v[n1 + 24];
+        v[n1] = add2(d0, d2);
+        v[n1 + 8] = add_mi(d1, e);
+        v[n1 + 16] = sub2(d0, d2);
+        v[n1 + 24] = sub_mi(d1, e);
+    }
+    fft8<1>(v);
+#pragma unroll
+    for (int k2 = 1; k2 < 4; k2++) {
+        f2 *u = v + 8 * k2;
+        // first layer of the 8-point FFT over n1 with the twiddles W32^(n1 k2) folded in
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const f2 aj = j == 0 ? u[0] : cmulc(u[j], c_w32[j * k2], c_w32r[j * k2]);
+            const int e4 = (j + 4) * k2;
+            if (e4 == 8) {   // W32^8 = -i
+                const f2 b = u[j + 4];
+                u[j] = add_mi(aj, b);
+                u[j + 4] = sub_mi(aj, b);
+            } else {
+                bfly_w(aj, u[j + 4], c_w32[e4], c_w32r[e4], u[j], u[j + 4]);
+            }
+        }
+        fft8_tail<1>(u);
+    }
+}
+// one predicated add: acc += pw where the lane's membership bit is set (LOP3 to a predicate + FADD)
+__device__ __forceinline__ void fold_add(float &acc, const float pw, const uint32_t m, const uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.rn.f32 %0, %0, %1;\n\t}"
+        : "+f"(acc) : "f"(pw), "r"(m), "r"(bit));
+}
+// split + power + chroma fold of bin k = L + 32 t, revision 2: w = W_4096^(L + 32 t) from shared memory
+__device__ __forceinline__ void tm_bin2(const int t, const f2 z, const f2 zp, const f2 w, const uint32_t (&fold_m)[4],
+                                        float (&acc)[FP_BANDS]) {
+    const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
+    const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
+    const f2 x = cmad_s(o, w, e);                    // 2 X[k] = 2E + W 2O
+    const float pw = __fmaf_rn(x.x, x.x, __fmul_rn(x.y, x.y));
+#define FOLDC(T, NOTE, IDX, LANES)                                                   \
+    if (t == T) {                                                                    \
+        if ((LANES) == 0xffffffffu) acc[NOTE] += pw;                                 \
+        else fold_add(acc[NOTE], pw, fold_m[(IDX) >> 5], 1u << ((IDX) & 31));        \
+    }
+#include "fp_chroma_fold.inc"
+#undef FOLDC
+}
+
 // split + power + chroma fold of bin k = L + 32 t (t is a compile-time constant after unrolling):
 // z = Z[k], zp = Z[2048 - k]
 __device__ __forceinline__ void tm_bin(const int t, const f2 z, const f2 zp, const f2 lw, const uint32_t (&fold_m)[4],
@@ -674,7 +785,7 @@ __device__ __forceinline__ void tm_bin(const int t, const f2 z, const f2 zp, con
 #undef FOLDC
 }
 
-template <int NW>
+template <int NW, int REV>
 __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Args a) {
     static_assert(NW % 4 == 0 && NW <= 16, "4 warps per TMEM lane quadrant, 128 columns each");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -683,12 +794,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
     unsigned char *s_warp = reinterpret_cast<unsigned char *>(s_twiddle + FP_HALF);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_warp + NW * TM_WARP_BYTES);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + NW);
+    f2 *s_wsplit = reinterpret_cast<f2 *>(s_tmem + 4);                   // REV >= 2: [41][32] W_4096^(L + 32 t)
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps what
+    // derives from it (TMEM addresses, barrier address) in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) {
         if (i < FP_HALF / 2) s_window[i] = a.window[i];
         s_twiddle[i] = a.twiddle[i];
+        if (REV >= 2 && i < FP_T * 32) s_wsplit[i] = a.wsplit[i];
     }
     if (threadIdx.x < NW) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -750,15 +865,38 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
             const uint32_t *ph = p + 32 * half;
             const f2 *wlo = s_window + 32 * half + lane;
             const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
+            if (REV >= 2) {
+                // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that)
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
-                const f2 s = s16x2_to_float(__funnelshift_r(w0, w1, shift));
-                const f2 wv = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
-                v[j] = mul2(s, wv);
+                for (int n1 = 0; n1 < 8; n1++) {
+                    f2 sv[4], wv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int j = n1 + 8 * i;
+                        const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                        sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
+                        wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                    }
+                    const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
+                    const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
+                    v[n1] = d0;
+                    v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
+                    v[n1 + 8] = d2;
+                    v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
+                }
+                if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
+                fft32_tail(v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                    const f2 s = s16x2_to_float(__funnelshift_r(w0, w1, shift));
+                    const f2 wv = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                    v[j] = mul2(s, wv);
+                }
+                if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
+                fft32(v);
             }
-            if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
-            fft32(v);
             if (half == 0) {
                 // E[k] sits in v[pos32(k)]; parked in register order (slot j = v[j])
 #pragma unroll
@@ -775,9 +913,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int k = c + 4 * i;   // pos32(k) = 8 c + i
-                        const f2 o = k == 0 ? v[8 * c + i] : cmulc(v[8 * c + i], c_w64[k], c_w64r[k]);
-                        sts2(lane_addr + k * ROW, sub2(e[i], o));   // Y[k + 32] -> row k
-                        e[i] = add2(e[i], o);                       // Y[k]      -> back to slot A
+                        if (REV >= 2 && k != 0) {
+                            f2 yp, ym;
+                            bfly_w(e[i], v[8 * c + i], c_w64[k], c_w64r[k], yp, ym);
+                            sts2(lane_addr + k * ROW, ym);              // Y[k + 32] -> row k
+                            e[i] = yp;                                  // Y[k]      -> back to slot A
+                        } else {
+                            const f2 o = k == 0 ? v[8 * c + i] : cmulc(v[8 * c + i], c_w64[k], c_w64r[k]);
+                            sts2(lane_addr + k * ROW, sub2(e[i], o));   // Y[k + 32] -> row k
+                            e[i] = add2(e[i], o);                       // Y[k]      -> back to slot A
+                        }
                     }
                     tmem_st8(tA + 16 * c, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
                 }
@@ -802,8 +947,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
             }
             const f2 *row = xchg + lane * XCHG_STRIDE;
             const f2 *tw = s_twiddle + lane + 32 * q;
+            if (REV >= 2) {
+                // twiddles and first radix-2 layer in one, scalar FFMA: c0 = r0 t0, c0 + r2 t2, 2 c0 - that
 #pragma unroll
-            for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul3(row[n2], tw[n2 * 64]);
+                for (int n1 = 0; n1 < 8; n1++) {
+                    const f2 c0 = n1 == 0 ? row[0] : cmul_s(row[n1], tw[n1 * 64]);
+                    const f2 c1 = cmul_s(row[n1 + 8], tw[(n1 + 8) * 64]);
+                    const f2 d0 = cmad_s(row[n1 + 16], tw[(n1 + 16) * 64], c0);
+                    const f2 d2 = cmad_s(row[n1 + 24], tw[(n1 + 24) * 64], c1);
+                    v[n1] = d0;
+                    v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
+                    v[n1 + 8] = d2;
+                    v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
+                }
+            } else {
+#pragma unroll
+                for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul3(row[n2], tw[n2 * 64]);
+            }
             __syncwarp();   // the rows are consumed
             if (q == 0) {
                 // the buffer is free: start the next frame's PCM on its way
@@ -819,7 +979,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                     }
                 }
             }
-            fft32(v);
+            if (REV >= 2) fft32_tail(v); else fft32(v);
             if (q == 1) {
                 // Z[L + 32 (2 k2 + 1)] parked in k2 order: slot B column 2 k2
 #pragma unroll
@@ -849,12 +1009,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                 const int a2 = 4 * g + i;
                 {   // t = 2 a: own register; partner's parked entry 31 - a
                     const f2 z = v[pos32(a2)];
+                    const f2 own = v[pos32(a2 == 0 ? 0 : 32 - a2)];   // lane 0: k = 32 t pairs with 32 (64 - t), even
                     f2 zp;
                     zp.x = __shfl_sync(0xffffffffu, pb[3 - i].x, partner);
                     zp.y = __shfl_sync(0xffffffffu, pb[3 - i].y, partner);
-                    const f2 own = v[pos32(a2 == 0 ? 0 : 32 - a2)];   // lane 0: k = 32 t pairs with 32 (64 - t), even
                     if (lane == 0) zp = own;
-                    tm_bin(2 * a2, z, zp, lw, fold_m, acc);
+                    if (REV >= 2) tm_bin2(2 * a2, z, zp, s_wsplit[(2 * a2) * 32 + lane], fold_m, acc); else tm_bin(2 * a2, z, zp, lw, fold_m, acc);
                 }
                 {   // t = 2 a + 1: own parked entry a; partner's register; lane 0: its own parked entry 31 - a
                     const f2 z = pa[i];
@@ -863,19 +1023,19 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                     zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
                     zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
                     if (lane == 0) zp = pb[3 - i];
-                    tm_bin(2 * a2 + 1, z, zp, lw, fold_m, acc);
+                    if (REV >= 2) tm_bin2(2 * a2 + 1, z, zp, s_wsplit[(2 * a2 + 1) * 32 + lane], fold_m, acc); else tm_bin(2 * a2 + 1, z, zp, lw, fold_m, acc);
                 }
             }
         }
         {   // t = 40: partner's parked entry 11
             const f2 p11 = tmem_ld1_wait(tB + 2 * 11);
             const f2 z = v[pos32(20)];
+            const f2 own = v[pos32(12)];
             f2 zp;
             zp.x = __shfl_sync(0xffffffffu, p11.x, partner);
             zp.y = __shfl_sync(0xffffffffu, p11.y, partner);
-            const f2 own = v[pos32(12)];
             if (lane == 0) zp = own;
-            tm_bin(40, z, zp, lw, fold_m, acc);
+            if (REV >= 2) tm_bin2(40, z, zp, s_wsplit[40 * 32 + lane], fold_m, acc); else tm_bin(40, z, zp, lw, fold_m, acc);
         }
         // 12 sums over 32 lanes with halving butterflies (as in the h32 kernel): 18 shuffles
         float r6[6], r3[3];
@@ -1298,6 +1458,11 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
         const double ang = -2.0 * PI * l / FP_FRAME;
         lane_w[l] = make_float2((float)cos(ang), (float)sin(ang));
     }
+    std::vector<float2> wsplit(FP_T * 32);
+    for (int k = 0; k < FP_T * 32; k++) {
+        const double ang = -2.0 * PI * k / FP_FRAME;
+        wsplit[k] = make_float2((float)cos(ang), (float)sin(ang));
+    }
     for (int e = 0; e < 64; e++) w64[e] = make_float2((float)cos(-2.0 * PI * e / 64), (float)sin(-2.0 * PI * e / 64));
     for (int e = 0; e < 32; e++) w32[e] = make_float2((float)cos(-2.0 * PI * e / 32), (float)sin(-2.0 * PI * e / 32));
     for (int t = 0; t < FP_T; t++)
@@ -1392,6 +1557,8 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpy(ctx->d_fp_window.p, window.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_twiddle.p, tw.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_lane.p, lane_w.data(), sizeof(float2) * 32, cudaMemcpyHostToDevice));
+    NB_TRY(ctx->d_fp_wsplit.alloc(sizeof(float2) * wsplit.size()));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_wsplit.p, wsplit.data(), sizeof(float2) * wsplit.size(), cudaMemcpyHostToDevice));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  K1_SMEM_BYTES));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1400,9 +1567,11 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
                                  h32_smem_bytes<10>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_h32_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  h32_smem_bytes<8>()));
-    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
-    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<16>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<12>()));
     ctx->fp_ready = true;
     return NB200_OK;
@@ -1507,6 +1676,7 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         k1.window = ctx->d_fp_window.as<float2>();
         k1.twiddle = ctx->d_fp_twiddle.as<float2>();
         k1.lane_w = ctx->d_fp_lane.as<float2>();
+        k1.wsplit = ctx->d_fp_wsplit.as<float2>();
         k1.chroma = ctx->d_chroma.as<float>();
         G4Args g;
         g.pcm = k1.pcm;
@@ -1522,17 +1692,19 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
             const uint32_t nf = f1 - f0;
-            const int variant = ctx->k1_variant == 0 ? 16 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM
+            const int variant = ctx->k1_variant == 0 ? 17 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM, revision-2 arithmetic
             if (variant >= 16) {
                 // tensor-memory kernel: 16 (or, variant 112, 12) warps per SM
                 k1.frame_begin = f0;
                 k1.frame_end = f1;
                 const uint32_t nw = variant == 112 ? 12u : 16u;
                 const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
-                if (nw == 16)
-                    fp_fft_chroma_tm_kernel<16><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                if (variant == 17)
+                    fp_fft_chroma_tm_kernel<16, 2><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                else if (nw == 16)
+                    fp_fft_chroma_tm_kernel<16, 1><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
                 else
-                    fp_fft_chroma_tm_kernel<12><<<grid1, 12 * 32, tm_smem_bytes<12>(), st>>>(k1);
+                    fp_fft_chroma_tm_kernel<12, 1><<<grid1, 12 * 32, tm_smem_bytes<12>(), st>>>(k1);
             } else if (variant >= 8) {
                 k1.frame_begin = f0;
                 k1.frame_end = f1;
@@ -1716,6 +1888,31 @@ int nb200_pcmset_upload(nb200_ctx *ctx, const int16_t *const *pcm, const uint64_
 }
 
 void nb200_pcmset_free(nb200_pcmset *ps) { delete ps; }
+
+int nb200_pcmset_view(nb200_ctx *ctx, const void *d_pcm, const uint64_t *dev_offset, const uint64_t *n_mono_samples,
+                      uint32_t n_segments, uint64_t capacity, nb200_pcmset **out) {
+    if (!ctx || !out || (n_segments && (!d_pcm || !dev_offset || !n_mono_samples))) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    if (reinterpret_cast<uintptr_t>(d_pcm) % 16 != 0) return NB200_ERR_INVALID_ARGUMENT;
+    nb200_pcmset *ps = new (std::nothrow) nb200_pcmset();
+    if (!ps) return NB200_ERR_TOO_LARGE;
+    ps->n_segments = n_segments;
+    ps->n_mono.assign(n_mono_samples, n_mono_samples + n_segments);
+    ps->dev_offset.assign(dev_offset, dev_offset + n_segments);
+    uint64_t end = 0;
+    for (uint32_t s = 0; s < n_segments; s++) {
+        // the bulk copy of a frame reads 16-byte units: up to 16 bytes beyond the frame's last sample
+        if (dev_offset[s] + n_mono_samples[s] + 8 > capacity) {
+            delete ps;
+            return NB200_ERR_INVALID_ARGUMENT;
+        }
+        end = std::max(end, dev_offset[s] + n_mono_samples[s]);
+    }
+    ps->dev_total = end;
+    ps->d_pcm.borrow(const_cast<void *>(d_pcm), (size_t)capacity * sizeof(int16_t));
+    *out = ps;
+    return NB200_OK;
+}
 
 int nb200_fingerprint_run(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
                           uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out) {

@@ -364,13 +364,7 @@ int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_
 // A rank's match output as one fixed-size message: 64-byte header, then DeviceRun records.
 // The match kernel emits straight into the records; this kernel fills in the header from
 // the match counters once the kernels before it on the stream are done.
-struct RunBlockHeader {
-    uint32_t n_found;    // runs the match found
-    uint32_t n_stored;   // min(n_found, capacity): the records that follow
-    uint32_t flags;      // bit 0: a Duration subtraction would have underflowed
-    uint32_t reserved[13];
-};
-static_assert(sizeof(RunBlockHeader) == 64, "header and records share one 64-byte grid");
+// (RunBlockHeader: common.h)
 
 __global__ void block_header_kernel(RunBlockHeader *h, const unsigned int *__restrict__ counters, uint32_t cap) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -424,13 +418,26 @@ int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, u
                       const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                       uint64_t n_pairs, const nb200_match_params *params, int do_vote,
                       nb200_search_result *results, uint64_t *max_found) {
+    if (block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0) return NB200_ERR_INVALID_ARGUMENT;
+    return vote_blocks_impl(ctx, d_blocks, n_blocks, block_bytes, (block_bytes - sizeof(RunBlockHeader)) / sizeof(DeviceRun),
+                            hash_duration_ns, n_videos, pairs, n_pairs, params, do_vote, results, max_found);
+}
+
+}  // extern "C"
+
+// The blocks may sit further apart than they are long (a receive area with fixed slots):
+// block_bytes = distance between block starts, cap = records a block can hold.
+int nb200::vote_blocks_impl(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes, uint64_t cap,
+                            const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
+                            uint64_t n_pairs, const nb200_match_params *params, int do_vote,
+                            nb200_search_result *results, uint64_t *max_found) {
     if (!ctx || !d_blocks || !hash_duration_ns || !params || !max_found) return NB200_ERR_NULL_ARGUMENT;
     if (do_vote && !results) return NB200_ERR_NULL_ARGUMENT;
-    if (n_blocks == 0 || block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0)
+    if (n_blocks == 0 || block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0 ||
+        sizeof(RunBlockHeader) + cap * sizeof(DeviceRun) > block_bytes)
         return NB200_ERR_INVALID_ARGUMENT;
     NB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const uint64_t cap = (block_bytes - sizeof(RunBlockHeader)) / sizeof(DeviceRun);
     const uint64_t total_cap = cap * n_blocks;
     if (total_cap >= 0x7fffffffull) return NB200_ERR_TOO_LARGE;
     *max_found = 0;
@@ -494,5 +501,3 @@ int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, u
     PhaseTimer pt(ctx, NB200_PHASE_VOTE);
     return vote_impl(hash_duration_ns, n_videos, pairs, n_pairs, params, runs.data(), raw.size(), nullptr, results);
 }
-
-}  // extern "C"

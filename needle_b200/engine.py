@@ -397,6 +397,18 @@ class PcmSet:
               "nb200_pcmset_upload")
         return PcmSet(ctx, out, n)
 
+    @staticmethod
+    def view(ctx: "Context", d_pcm: int, dev_offset, n_mono, capacity: int, keepalive=None) -> "PcmSet":
+        """nb200_pcmset_view: mono S16 PCM that is already in device memory (caller-owned)."""
+        off = np.ascontiguousarray(dev_offset, dtype=np.uint64)
+        cnt = np.ascontiguousarray(n_mono, dtype=np.uint64)
+        out = C.c_void_p()
+        check(lib().nb200_pcmset_view(ctx.handle, C.c_void_p(d_pcm), ptr(off), ptr(cnt), cnt.size, capacity,
+                                      C.byref(out)), "nb200_pcmset_view")
+        ps = PcmSet(ctx, out, cnt.size)
+        ps._keepalive = keepalive
+        return ps
+
     def fingerprint(self, stride: int = 2, delay_ns: int = DELAY_NS, item_ns: int = ITEM_NS,
                     seek_to_ns=None) -> HashSet:
         seek = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
@@ -454,3 +466,138 @@ class PinnedArray:
             self.array = None
             check(lib().nb200_host_free(C.c_void_p(self._ptr)), "nb200_host_free")
             self._ptr = 0
+
+
+# ------------------------------------------------------------------ multi-GPU jobs (nb200_comm / nb200_mjob)
+
+MJOB_PHASES = ("fingerprint", "hash_allgather", "match", "run_push_wait", "vote")
+
+
+def comm_unique_id() -> bytes:
+    """nb200_comm_unique_id: 128 bytes that rank 0 hands to every process of the job."""
+    buf = (C.c_uint8 * 128)()
+    check(lib().nb200_comm_unique_id(buf), "nb200_comm_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    """nb200_comm: one rank of a multi-GPU job (a context + its NCCL communicator)."""
+
+    def __init__(self, ctx: Context, handle, rank: int, world: int):
+        self.ctx, self._h, self.rank, self.world = ctx, handle, rank, world
+
+    @staticmethod
+    def init_rank(ctx: Context, unique_id: bytes | None, rank: int, world: int) -> "Comm":
+        """One process per GPU: every process calls this with the id rank 0 made."""
+        out = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        check(lib().nb200_comm_init_rank(ctx.handle, idbuf, rank, world, C.byref(out)), "nb200_comm_init_rank")
+        return Comm(ctx, out, rank, world)
+
+    @staticmethod
+    def init_all(ctxs) -> list:
+        """One process, N devices (ncclCommInitAll): the shape of needle itself."""
+        n = len(ctxs)
+        hs = (C.c_void_p * n)(*[c.handle for c in ctxs])
+        out = (C.c_void_p * n)()
+        check(lib().nb200_comm_init_all(hs, n, out), "nb200_comm_init_all")
+        return [Comm(ctxs[r], C.c_void_p(out[r]), r, n) for r in range(n)]
+
+    def destroy(self):
+        if self._h:
+            lib().nb200_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class MultiJob:
+    """nb200_mjob: a search-only or analyze+search job over all ranks; `comms` = the ranks this
+    process drives (one under torchrun, all of them in a single-process host)."""
+
+    def __init__(self, comms, handle, n_videos: int, n_segments_pcm: int = 0):
+        self.comms, self._h, self.n_videos = list(comms), handle, n_videos
+        self.has_rank0 = any(c.rank == 0 for c in self.comms)
+        self._n_seg = n_segments_pcm
+        self._keep = None
+
+    @staticmethod
+    def _comm_array(comms):
+        return (C.c_void_p * len(comms))(*[c._h for c in comms])
+
+    @staticmethod
+    def search(comms, hashes, ts_ns, seg_offset, hash_duration_ns, params: MatchParams, pairs=None) -> "MultiJob":
+        h = np.ascontiguousarray(hashes, dtype=np.uint32)
+        t = np.ascontiguousarray(ts_ns, dtype=np.uint64)
+        off = np.ascontiguousarray(seg_offset, dtype=np.uint64)
+        n_videos = (off.size - 1) // 2
+        hd = np.ascontiguousarray(np.broadcast_to(np.asarray(hash_duration_ns, dtype=np.uint64), (n_videos,)))
+        _keep, pp, npairs = _pairs_arg(pairs)
+        out = C.c_void_p()
+        check(lib().nb200_mjob_search_create(MultiJob._comm_array(comms), len(comms), ptr(h), ptr(t), ptr(off), n_videos,
+                                             ptr(hd), pp, npairs, C.byref(params), C.byref(out)),
+              "nb200_mjob_search_create")
+        return MultiJob(comms, out, n_videos)
+
+    @staticmethod
+    def season(comms, n_mono_per_segment, seek_to_ns, hash_duration_ns: int, params: MatchParams,
+               pairs=None) -> "MultiJob":
+        nm = np.ascontiguousarray(n_mono_per_segment, dtype=np.uint64)
+        n_videos = nm.size // 2
+        sk = None if seek_to_ns is None else np.ascontiguousarray(seek_to_ns, dtype=np.uint64)
+        _keep, pp, npairs = _pairs_arg(pairs)
+        out = C.c_void_p()
+        check(lib().nb200_mjob_season_create(MultiJob._comm_array(comms), len(comms), ptr(nm), ptr(sk), n_videos,
+                                             int(hash_duration_ns), pp, npairs, C.byref(params), C.byref(out)),
+              "nb200_mjob_season_create")
+        return MultiJob(comms, out, n_videos, nm.size)
+
+    def video_rank(self) -> np.ndarray:
+        out = np.zeros(self.n_videos, np.uint32)
+        check(lib().nb200_mjob_video_rank(self._h, ptr(out)), "nb200_mjob_video_rank")
+        return out
+
+    def _pcm_ptrs(self, segments):
+        """segments: {global segment id: int16 array} (or a full list); others stay NULL."""
+        arr = (C.c_void_p * max(self._n_seg, 1))()
+        keep = []
+        items = segments.items() if isinstance(segments, dict) else enumerate(segments)
+        for s, x in items:
+            if x is None:
+                continue
+            a = x if (isinstance(x, np.ndarray) and x.dtype == np.int16 and x.flags.c_contiguous) else \
+                np.ascontiguousarray(x, dtype=np.int16)
+            keep.append(a)
+            arr[s] = a.ctypes.data
+        return arr, keep
+
+    def upload_pcm(self, segments):
+        arr, keep = self._pcm_ptrs(segments)
+        check(lib().nb200_mjob_upload_pcm(self._h, arr), "nb200_mjob_upload_pcm")
+
+    def run(self, host_segments=None):
+        """One pass.  Returns the per-video result tuples where rank 0 is local, else None."""
+        arr, keep = (None, None) if host_segments is None else self._pcm_ptrs(host_segments)
+        res = (SearchResultC * max(self.n_videos, 1))() if self.has_rank0 else None
+        check(lib().nb200_mjob_run(self._h, arr, res), "nb200_mjob_run")
+        return _results_list(res, self.n_videos) if self.has_rank0 else None
+
+    def phase_ms(self) -> dict:
+        ms = (C.c_float * len(MJOB_PHASES))()
+        check(lib().nb200_mjob_phase_ms(self._h, ms), "nb200_mjob_phase_ms")
+        return dict(zip(MJOB_PHASES, [float(x) for x in ms]))
+
+    def free(self):
+        if self._h:
+            lib().nb200_mjob_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
