@@ -182,6 +182,7 @@ struct nb200_comm {
     char *peer_recv0 = nullptr;               // rank 0's receive area as seen from this rank
     AckTargets ack_targets = {};              // rank 0: every rank's control block
     std::vector<void *> ipc_opened;           // to close
+    std::vector<void *> retired;              // rank 0: receive areas replaced by larger ones
     uint32_t step = 0;
     nb200::PinnedBuf h_ack;
     bool tail_ready = false;
@@ -226,6 +227,7 @@ void nb200_comm_destroy(nb200_comm *c) {
     if (c->nccl && nccl_api().ok) nccl_api().CommDestroy(c->nccl);
     if (c->d_ctrl) cudaFree(c->d_ctrl);
     if (c->d_recv) cudaFree(c->d_recv);
+    for (void *p : c->retired) cudaFree(p);
     delete c;
 }
 
@@ -512,6 +514,72 @@ static int mjob_alloc_blocks(nb200_mjob *j) {
     return NB200_OK;
 }
 
+// Rank 0's receive area has one fixed slot per rank; a step whose run blocks outgrow the slots
+// (every rank learns the same run count from the acknowledgement) replaces the area.  Collective:
+// every rank calls it at the same point with the same size; all streams are idle then.
+static int grow_recv(nb200_mjob *j, uint64_t need_bytes) {
+    uint64_t bytes = j->ranks[0].comm->recv_block_bytes;
+    while (bytes < need_bytes) bytes *= 2;
+    if (bytes > (1ull << 30)) {
+        set_last_error_msg("a rank's run block exceeds 1 GiB");
+        return NB200_ERR_TOO_LARGE;
+    }
+    const int world = j->world;
+    nb200_comm *c0 = nullptr;
+    for (auto &R : j->ranks)
+        if (R.comm->rank == 0) c0 = R.comm;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    if (c0) {
+        NB_CUDA(cudaSetDevice(c0->ctx->device));
+        NB_CUDA(cudaStreamSynchronize(c0->ctx->stream));
+        // the old area stays allocated until the comm goes: other processes may still have it mapped
+        c0->retired.push_back(c0->d_recv);
+        c0->d_recv = nullptr;
+        NB_CUDA(cudaMalloc(&c0->d_recv, (size_t)world * bytes));
+        c0->peer_recv0 = c0->d_recv;
+    }
+    if (j->ranks[0].comm->single_process) {
+        for (auto &R : j->ranks) {
+            R.comm->peer_recv0 = c0->d_recv;
+            R.comm->recv_block_bytes = bytes;
+        }
+        return NB200_OK;
+    }
+    // one process per rank: the new area's IPC handle travels the way the first one did
+    nb200_comm *c = j->ranks[0].comm;
+    nb200_ctx *ctx = c->ctx;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    if (c->rank == 0) NB_CUDA(cudaIpcGetMemHandle(&mine, c->d_recv));
+    DevBuf d_send, d_all;
+    std::vector<cudaIpcMemHandle_t> all((size_t)world);
+    NB_TRY(d_send.alloc(sizeof(mine)));
+    NB_TRY(d_all.alloc(sizeof(mine) * world));
+    NB_CUDA(cudaMemcpyAsync(d_send.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    NB_NCCL(nccl_api().AllGather(d_send.p, d_all.p, sizeof(mine), ncclUint8, c->nccl, ctx->stream));
+    NB_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(mine) * world, cudaMemcpyDeviceToHost, ctx->stream));
+    NB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (c->rank != 0) {
+        // the old mapping is the last one this rank opened for rank 0's receive area
+        for (size_t k = 0; k < c->ipc_opened.size(); k++)
+            if (c->ipc_opened[k] == c->peer_recv0) {
+                cudaIpcCloseMemHandle(c->peer_recv0);
+                c->ipc_opened.erase(c->ipc_opened.begin() + (long)k);
+                break;
+            }
+        void *q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, all[0], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_last_error("cudaIpcOpenMemHandle(grown receive area)", e);
+            return NB200_ERR_CUDA;
+        }
+        c->ipc_opened.push_back(q);
+        c->peer_recv0 = (char *)q;
+    }
+    c->recv_block_bytes = bytes;
+    return NB200_OK;
+}
+
 // The part after "every rank holds the whole season": match this rank's slice, push, vote on rank 0.
 // Phases over the local ranks so that ONE host thread can drive all of them (single-process mode):
 // nothing that rank 0 waits for may sit behind a host wait of another local rank.
@@ -520,10 +588,7 @@ static int mjob_tail(nb200_mjob *j, nb200_search_result *results) {
     const uint32_t(*pairs)[2] = reinterpret_cast<const uint32_t(*)[2]>(j->pairs.data());
     for (int attempt = 0; attempt < 8; attempt++) {
         const uint64_t block_bytes = 64 * (1 + j->run_cap);
-        if (world > 1 && block_bytes > j->ranks[0].comm->recv_block_bytes) {
-            set_last_error_msg("a rank's run block exceeds the peer receive area (16 MiB per rank)");
-            return NB200_ERR_TOO_LARGE;
-        }
+        if (world > 1 && block_bytes > j->ranks[0].comm->recv_block_bytes) NB_TRY(grow_recv(j, block_bytes));
         // ---- A: every local rank matches its slice into its block and pushes it to rank 0
         for (auto &R : j->ranks) {
             nb200_comm *c = R.comm;
