@@ -451,6 +451,12 @@ enum {
 };
 int nb200_mjob_phase_ms(const nb200_mjob *job, float *ms /* [NB200_MJOB_PHASES] */);
 void nb200_mjob_free(nb200_mjob *job);
+/* The jobs' sharding rules on their own (host only, no device needed): which rank fingerprints
+ * which video (greedy by sample count, n_mono_samples[2 * n_videos]), and where the pair list
+ * is cut (cuts[world + 1], slices balanced by table cells; pairs == NULL: all i < j). */
+int nb200_plan_videos(const uint64_t *n_mono_samples, uint32_t n_videos, int world, uint32_t *rank_of_video);
+int nb200_plan_pairs(const uint64_t *seg_len, uint32_t n_videos, const uint32_t (*pairs)[2], uint64_t n_pairs, int world,
+                     int include_endings, uint64_t *cuts);
 
 /* ------------------------------------------------------------ persistence */
 

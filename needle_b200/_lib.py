@@ -157,6 +157,8 @@ PROTOTYPES = {
     "nb200_mjob_run": (C.c_int, [_P, _P, C.POINTER(SearchResultC)]),
     "nb200_mjob_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "nb200_mjob_free": (None, [_P]),
+    "nb200_plan_videos": (C.c_int, [_P, C.c_uint32, C.c_int, _P]),
+    "nb200_plan_pairs": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64, C.c_int, C.c_int, _P]),
     "nb200_framehashes_write": (C.c_int, [C.c_char_p, _P, _P, C.c_uint64, _P, _P, C.c_uint64,
                                           C.c_uint64, C.c_char_p]),
     "nb200_framehashes_read": (C.c_int, [C.c_char_p, _PP, _PP, _U64P, _PP, _PP, _U64P, _U64P,

@@ -425,6 +425,23 @@ static void shard_pairs(const std::vector<uint64_t> &seg_len, const uint32_t *pa
     cuts[world] = n_pairs;
 }
 
+// videos -> ranks: longest first onto the least loaded rank, ties to the lower video / rank
+// (every rank computes the same plan from the same sample counts)
+static void plan_videos(const uint64_t *n_mono, uint32_t n_videos, int world, uint32_t *rank_of_video) {
+    std::vector<uint32_t> order(n_videos);
+    std::iota(order.begin(), order.end(), 0u);
+    auto cost = [&](uint32_t v) { return n_mono[2 * v] + n_mono[2 * v + 1]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
+    std::vector<uint64_t> load(world, 0);
+    for (uint32_t v : order) {
+        int best = 0;
+        for (int r = 1; r < world; r++)
+            if (load[r] < load[best]) best = r;
+        rank_of_video[v] = (uint32_t)best;
+        load[best] += cost(v);
+    }
+}
+
 static uint64_t stored_hashes(uint64_t n_mono, uint32_t stride) {
     const uint64_t raw = nb200_num_raw_hashes(n_mono);
     return (raw + stride - 1) / stride;
@@ -786,20 +803,8 @@ int nb200_mjob_season_create(nb200_comm *const *comms, int n_local, const uint64
     if (seek_to_ns) j->seek_to_ns.assign(seek_to_ns, seek_to_ns + nseg);
     j->seg_len.resize(nseg);
     for (size_t s = 0; s < nseg; s++) j->seg_len[s] = stored_hashes(j->n_mono[s], j->stride);
-    // videos -> ranks: longest first onto the least loaded rank (every rank computes the same plan)
-    std::vector<uint32_t> order(n_videos);
-    std::iota(order.begin(), order.end(), 0u);
-    auto cost = [&](uint32_t v) { return j->n_mono[2 * v] + j->n_mono[2 * v + 1]; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost(a) > cost(b); });
-    std::vector<uint64_t> load(world, 0);
     j->video_rank.assign(n_videos, 0);
-    for (uint32_t v : order) {
-        int best = 0;
-        for (int r = 1; r < world; r++)
-            if (load[r] < load[best]) best = r;
-        j->video_rank[v] = (uint32_t)best;
-        load[best] += cost(v);
-    }
+    plan_videos(j->n_mono.data(), n_videos, world, j->video_rank.data());
     // each rank's block of the exchange buffers is laid out like a hashset of its own segments
     std::vector<std::vector<uint32_t>> segs_of(world);
     for (uint32_t v = 0; v < n_videos; v++) {
@@ -935,6 +940,30 @@ int nb200_mjob_run(nb200_mjob *j, const int16_t *const *host_pcm, nb200_search_r
 int nb200_mjob_phase_ms(const nb200_mjob *j, float *ms) {
     if (!j || !ms) return NB200_ERR_NULL_ARGUMENT;
     memcpy(ms, j->phase_ms, sizeof(j->phase_ms));
+    return NB200_OK;
+}
+
+/* Host-only: the sharding rules of the jobs above, for hosts that want to know them in advance
+ * (which PCM to decode where) and for tests. */
+int nb200_plan_videos(const uint64_t *n_mono_samples, uint32_t n_videos, int world, uint32_t *rank_of_video) {
+    if ((!n_mono_samples || !rank_of_video) && n_videos) return NB200_ERR_NULL_ARGUMENT;
+    if (world < 1) return NB200_ERR_INVALID_ARGUMENT;
+    plan_videos(n_mono_samples, n_videos, world, rank_of_video);
+    return NB200_OK;
+}
+
+int nb200_plan_pairs(const uint64_t *seg_len, uint32_t n_videos, const uint32_t (*pairs)[2], uint64_t n_pairs, int world,
+                     int include_endings, uint64_t *cuts) {
+    if (!seg_len || !cuts) return NB200_ERR_NULL_ARGUMENT;
+    if (world < 1) return NB200_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> flat;
+    if (pairs) flat.assign(&pairs[0][0], &pairs[0][0] + 2 * n_pairs);
+    else all_pairs(n_videos, flat);
+    for (uint32_t v : flat)
+        if (v >= n_videos) return NB200_ERR_INVALID_ARGUMENT;
+    std::vector<uint64_t> len(seg_len, seg_len + 2 * (size_t)n_videos), c;
+    shard_pairs(len, flat.data(), flat.size() / 2, world, include_endings != 0, c);
+    memcpy(cuts, c.data(), sizeof(uint64_t) * (world + 1));
     return NB200_OK;
 }
 

@@ -1,17 +1,23 @@
-"""Multi-GPU flow: one process per GPU (torch.distributed; NCCL over NVLink on
-the box, gloo in CPU tests).
+"""Host-side mirror of the multi-GPU job, for CPU tests.
+
+The product's multi-GPU path is behind the C ABI (nb200_comm_* / nb200_mjob_*,
+csrc/multi.cu; engine.Comm / engine.MultiJob): one process driving N devices or one
+process per device, the library issuing the hash all-gather (NCCL) and pushing the run
+blocks to rank 0 over peer memory itself.  `comm_from_torch` below is all a torchrun
+host needs.
 
   episodes --shard--> fingerprint (K1/K2)        no collective
   hashes   --ONE all-gather--> every rank holds the whole season (KB..MB)
   pairs    --shard--> match (K3/K4)              no collective
-  runs     --gather--> rank 0, host vote (find_best_match)
+  runs     --gather--> rank 0, vote (find_best_match)
 
 which is how the reference's two rayon par_iter loops (per video,
-needle/src/audio/analyzer.rs:437-445; per pair, comparator.rs:549-564) map to
-ranks.  Everything that decides *what* each rank does (plans, offsets, run
-merging) is plain host code here and is exercised with world_size-2 gloo tests;
-the compute itself is behind the `Backend` protocol -- the product backend is
-`GpuBackend` (libneedle_b200.so), tests plug a checker in.
+needle/src/audio/analyzer.rs:437-445; per pair, comparator.rs:549-564) map to ranks.
+None of that can run without GPUs, so the same flow is written out here in plain Python
+over a `Backend` protocol: world_size-2 gloo tests (tests/test_dist_cpu.py) run it with
+the oracle playing the compute, and check that the sharding rules here (videos by sample
+count, pair slices by table cells, buffer layout) are the library's own
+(nb200_plan_videos, nb200_plan_pairs, nb200_fingerprint_layout).
 """
 from __future__ import annotations
 
@@ -140,153 +146,26 @@ def globalize_runs(runs: np.ndarray, slice_start: int) -> np.ndarray:
     return runs
 
 
-def bind_host_to_gpu_numa(device_index: int) -> bool:
-    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned
-    PCM buffers it allocates afterwards are first-touched on that NUMA node and the H2D copies
-    of several ranks do not all cross the same socket link.  Best effort: False if NVML or the
-    affinity call is unavailable."""
-    import os
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        try:
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[device_index]) if vis and vis.replace(",", "").isdigit() else device_index
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            words = (os.cpu_count() + 63) // 64
-            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
-            cpus &= set(os.sched_getaffinity(0))
-            if not cpus:
-                return False
-            os.sched_setaffinity(0, cpus)
-            return True
-        finally:
-            pynvml.nvmlShutdown()
-    except Exception:
-        return False
-
-
-class GpuBackend:
-    """The product compute path: libneedle_b200.so on this rank's GPU, running
-    on torch's current stream so that NCCL collectives order with the kernels."""
-
-    def __init__(self, device_index: int):
-        import torch
-        from . import engine
-        self.torch = torch
-        self.engine = engine
-        self.device = torch.device("cuda", device_index)
-        torch.cuda.set_device(self.device)
-        self.ctx = engine.Context(device_index)
-        # One real stream for the library's kernels AND torch's collectives: torch's default
-        # stream is the NULL stream, which the library's non-blocking stream would not be ordered
-        # with.  Every method that touches torch tensors runs under `with self._on_stream()`.
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.ctx.set_stream(self.stream.cuda_stream)
-        # the *_into fingerprint calls only enqueue: the job synchronises once, after the vote
-        self.ctx.set_option(engine.Context.OPT_DEFER_WAIT, 1)
-        self._run_bufs = None
-
-    def _on_stream(self):
-        return self.torch.cuda.stream(self.stream)
-
-    def upload_hashes(self, hashes, ts_ns, seg_offset):
-        """A whole library of precomputed hashes (KB..MB) on this rank's GPU."""
-        return self.engine.HashSet.upload(self.ctx, hashes, ts_ns, seg_offset)
-
-    def upload_pcm(self, segments):
-        return self.engine.PcmSet.upload(self.ctx, segments)
-
-    def fingerprint_search(self, pcmset, plan: SeasonPlan, seek_to_ns, hash_duration_ns, params):
-        """Single-GPU path: nb200_pcmset_search (K1, K2, match, simhash and the vote enqueued back
-        to back, one host wait); two calls when the videos' hash durations differ."""
-        hd = np.asarray(hash_duration_ns, dtype=np.uint64)
-        if hd.size and np.all(hd == hd[0]) and int(hd[0]) // 1_000_000 // 123 == plan.stride:
-            return pcmset.search(seek_to_ns, int(hd[0]), params)
-        hs = pcmset.fingerprint(stride=plan.stride, seek_to_ns=seek_to_ns)
-        try:
-            return hs.search(hash_duration_ns, params)
-        finally:
-            hs.free()
-
-    def alloc_exchange(self, plan: SeasonPlan):
-        t = self.torch
-        with self._on_stream():
-            return {"hash_send": t.zeros(plan.cap, dtype=t.int32, device=self.device),
-                    "ts_send": t.zeros(plan.cap, dtype=t.int64, device=self.device),
-                    "hash_recv": t.zeros(plan.cap * plan.world, dtype=t.int32, device=self.device),
-                    "ts_recv": t.zeros(plan.cap * plan.world, dtype=t.int64, device=self.device)}
-
-    def fingerprint_into(self, pcmset, plan: SeasonPlan, seek_to_ns, ex):
-        """K1/K2 on this rank's segments, written directly into the send buffers."""
-        pcmset.fingerprint_into(ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
-                                stride=plan.stride, seek_to_ns=seek_to_ns)
-
-    def fingerprint_host_into(self, segments, plan: SeasonPlan, seek_to_ns, ex):
-        """Host PCM -> (H2D in chunks underneath K1) -> K2 into the send buffers."""
-        self.ctx.fingerprint_host_into(segments, ex["hash_send"].data_ptr(), ex["ts_send"].data_ptr(), plan.cap,
-                                       stride=plan.stride, seek_to_ns=seek_to_ns)
-
-    def exchange(self, dist, ex, plan: SeasonPlan, seek_to_ns, group=None):
-        """ONE collective: the hashes.  Timestamps are a function of the index
-        (analyzer.rs:309), so every rank fills in all of them itself."""
-        # the timestamps do not depend on anyone's hashes: filled first, while slower ranks are still
-        # fingerprinting, so that nothing but the match stands behind the collective
-        self.ctx.timestamps_fill(ex["ts_recv"].data_ptr(), plan.dev_offset, plan.seg_len, seek_to_ns,
-                                 stride=plan.stride)
-        with self._on_stream():
-            dist.all_gather_into_tensor(ex["hash_recv"], ex["hash_send"], group=group)
-
-    def season_from_gathered(self, ex, plan: SeasonPlan, world: int):
-        h, t = (ex["hash_recv"], ex["ts_recv"]) if world > 1 else (ex["hash_send"], ex["ts_send"])
-        return self.engine.HashSet.view(self.ctx, h.data_ptr(), t.data_ptr(), plan.dev_offset, plan.seg_len,
-                                        keepalive=(h, t))
-
-    # ---- device-resident tail: runs never visit the host ------------------------------------
-    def run_block_capacity(self, slices) -> int:
-        """Run records per rank block: the same on every rank (it sizes the collective)."""
-        cap = getattr(self, "_block_cap", 0)
-        need = max(4096, 16 * max((e - s) for s, e in slices))
-        while cap < need:
-            cap = max(4096, cap * 2)
-        self._block_cap = cap
-        return cap
-
-    def search_gathered(self, dist, season, params, my_pairs, pair_base, all_pairs, hash_duration_ns, slices,
-                        group=None):
-        """match (this rank's slice, emitted straight into its run block) -> ONE all-gather of
-        the blocks -> heap replay + find_best_match on rank 0's GPU -> 48 bytes per video come
-        back.  One host wait per job; if a block overflowed every rank sees it in the gathered
-        headers and the step is repeated with larger blocks."""
-        t = self.torch
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        while True:
-            cap = self.run_block_capacity(slices)
-            block = 64 * (1 + cap)
-            with self._on_stream():
-                if self._run_bufs is None or self._run_bufs[0].numel() != block:
-                    self._run_bufs = (t.zeros(block, dtype=t.uint8, device=self.device),
-                                      t.zeros(block * world, dtype=t.uint8, device=self.device))
-                send, recv = self._run_bufs
-                season.match_export(params, my_pairs, pair_base, send.data_ptr(), block)
-                dist.all_gather_into_tensor(recv, send, group=group)
-            results, found, truncated = self.ctx.vote_blocks(recv.data_ptr(), world, block, hash_duration_ns, params,
-                                                             pairs=all_pairs, do_vote=(rank == 0))
-            if not truncated:
-                return results
-            self._block_cap = max(self._block_cap * 2, int(found))
-
-    def match(self, season, params, pairs) -> np.ndarray:
-        if len(pairs) == 0:
-            return np.zeros(0, dtype=RUN_DTYPE)
-        rs = season.match(params, pairs=pairs)
-        runs = rs.download()
-        rs.free()
-        return runs
-
-    def release(self, obj):
-        obj.free()
+def comm_from_torch(ctx, dist, device=None, group=None):
+    """One nb200_comm per process from a torch.distributed process group: rank 0 makes NCCL's unique
+    id (nb200_comm_unique_id), torch carries the 128 bytes, every rank joins
+    (nb200_comm_init_rank).  From here on the collectives are the library's own."""
+    from . import engine
+    if dist is None:
+        return engine.Comm.init_rank(ctx, None, 0, 1)
+    import torch
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        buf = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = buf.cpu().numpy().tobytes()
+    else:
+        box = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = box[0]
+    return engine.Comm.init_rank(ctx, uid, rank, world)
 
 
 def results_rows_as_tuples(arr: np.ndarray):
@@ -446,7 +325,7 @@ class SeasonJob:
 
     def run_host(self, local_segments):
         """From host PCM (pinned for full PCIe rate).  The copy is pipelined under K1
-        when the backend can stream (GpuBackend.fingerprint_host_into)."""
+        when the backend can stream (a fingerprint_host_into method)."""
         b = self.backend
         one_gpu = self.world == 1 and self._all_pairs and hasattr(b, "fingerprint_search")
         if one_gpu or not hasattr(b, "fingerprint_host_into"):

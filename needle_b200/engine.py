@@ -601,3 +601,21 @@ class MultiJob:
             self.free()
         except Exception:
             pass
+
+
+def plan_videos(n_mono_per_segment, world: int) -> np.ndarray:
+    """nb200_plan_videos: rank that fingerprints each video in a multi-GPU season job (host only)."""
+    nm = np.ascontiguousarray(n_mono_per_segment, dtype=np.uint64)
+    out = np.zeros(nm.size // 2, np.uint32)
+    check(lib().nb200_plan_videos(ptr(nm), nm.size // 2, world, ptr(out)), "nb200_plan_videos")
+    return out
+
+
+def plan_pairs(seg_len, world: int, include_endings: bool, pairs=None) -> np.ndarray:
+    """nb200_plan_pairs: cuts[world + 1] of the pair list, slices balanced by table cells (host only)."""
+    sl = np.ascontiguousarray(seg_len, dtype=np.uint64)
+    _keep, pp, npairs = _pairs_arg(pairs)
+    cuts = np.zeros(world + 1, np.uint64)
+    check(lib().nb200_plan_pairs(ptr(sl), sl.size // 2, pp, npairs, world, 1 if include_endings else 0, ptr(cuts)),
+          "nb200_plan_pairs")
+    return cuts

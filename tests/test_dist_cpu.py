@@ -51,12 +51,23 @@ def test_plans_cover_everything_once():
         sl = nd.shard_pairs(plan.seg_len, pairs, world, True)
         assert sl[0][0] == 0 and sl[-1][1] == len(pairs)
         assert all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        # ... and so are the sharding rules (multi.cu: nb200_plan_videos / nb200_plan_pairs)
+        want = np.zeros(13, np.uint32)
+        for r, vs in enumerate(plan.videos_of_rank):
+            want[vs] = r
+        assert engine.plan_videos(n_mono, world).tolist() == want.tolist()
+        for endings in (False, True):
+            sl = nd.shard_pairs(plan.seg_len, pairs, world, endings)
+            assert engine.plan_pairs(plan.seg_len, world, endings).tolist() == [a for a, _ in sl] + [len(pairs)]
+        sub = pairs[::3]
+        sl = nd.shard_pairs(plan.seg_len, sub, world, True)
+        assert engine.plan_pairs(plan.seg_len, world, True, pairs=sub).tolist() == [a for a, _ in sl] + [len(sub)]
     loads = [sum(int(n_mono[2 * v] + n_mono[2 * v + 1]) for v in vs) for vs in nd.SeasonPlan.build(n_mono, 4).videos_of_rank]
     assert max(loads) - min(loads) <= int(n_mono.reshape(-1, 2).sum(1).max())
 
 
 class OracleBackend:
-    """TEST-ONLY stand-in for GpuBackend: same interface, compute by the oracle."""
+    """TEST-ONLY backend of the dist.py mirror: compute by the oracle."""
 
     def __init__(self):
         import torch
@@ -118,7 +129,7 @@ class OracleBackend:
         return H.rows_to_runs(rows)
 
     def gather_runs(self, dist, runs, group=None):
-        """Same protocol as GpuBackend.gather_runs, on CPU tensors."""
+        """Pad-and-all-gather of the run lists, on CPU tensors."""
         t = self.torch
         world = dist.get_world_size(group)
         cnts = t.zeros(world, dtype=t.int64)

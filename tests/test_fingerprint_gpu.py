@@ -97,6 +97,15 @@ def test_silence_and_full_scale(ctx, oracle):
     assert agreement(ctx.fingerprint_batch([sq])[0], oracle.fingerprint(sq)) >= FRAME_AGREEMENT
 
 
+def test_upstream_chromaprint_silence_known_answer(ctx):
+    """Chromaprint's own API test (tests/test_api.cpp, Test2SilenceRawFp): 130 x 1024 zero samples at
+    44100 Hz -> raw fingerprint [627964279] * 3.  At 11025 Hz that input is 33280 zeros.  The literal
+    is upstream's, not the oracle's (tests/test_oracle_kat.py)."""
+    for channels in (1, 2):
+        pcm = np.zeros(33280 * channels, np.int16)
+        assert ctx.fingerprint_batch([pcm], channels=channels)[0].tolist() == [627964279] * 3
+
+
 def test_stride_and_timestamps_exact(ctx, oracle):
     """The subsample/timestamp tail of process_frames (analyzer.rs:288-318) is integer/f32-exact."""
     pcm_o = make_pcm(30, 95.0)

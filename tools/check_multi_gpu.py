@@ -102,10 +102,9 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         dist.init_process_group("gloo")
-        box = [engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
+        from needle_b200 import dist as nd
         ctx = engine.Context(local)
-        comm = engine.Comm.init_rank(ctx, box[0], rank, world)
+        comm = nd.comm_from_torch(ctx, dist)
         out = run_jobs([comm], n_videos, segs, seeks, params, pairs, season, params0)
         if rank == 0:
             compare(out, *single_gpu_truth(local, n_videos, segs, seeks, params, pairs, season, params0))
