@@ -83,11 +83,13 @@ int nb200_ctx_last_vote_ms(nb200_ctx *ctx, float *ms);
  * lengths >= 63 cells) would be chosen.  Results are identical either way. */
 enum {
     NB200_OPT_FORCE_GENERAL_MATCH = 1,
-    /* NB200_OPT_K1_VARIANT: 0 = the default (12).  8, 10, 12 = one warp per FFT frame, 32 complex
-     * values per lane (the other half parked in shared memory), that many warps per SM; 1 = one
-     * warp per frame with all 64 values per lane in registers (8 warps per SM); 4, 5, 6 = four
-     * warps per frame with that many frames in flight per CTA.  Same hashes up to FP32 rounding
-     * order (>= 99.99 % identical frames); a tuning switch. */
+    /* NB200_OPT_K1_VARIANT: which fingerprint FFT kernel runs (all: one warp per 4096-sample frame, at
+     * most 32 complex values per lane; same hashes up to FP32 rounding order, >= 99.99 % identical
+     * frames; a tuning switch).  0 = the default (17).  17 = tensor-memory kernel: the parked half of
+     * a frame lives in TMEM (tcgen05.st / tcgen05.ld), 16 warps per SM, FMA-fused butterflies;
+     * 16 / 112 = the same with the first revision of the arithmetic, 16 / 12 warps per SM;
+     * 8, 10, 12 = the parked half in shared memory, that many warps per SM; 1 = all 64 values of a
+     * lane in registers (8 warps per SM). */
     NB200_OPT_K1_VARIANT = 2,
     /* NB200_OPT_MATCH_DENSE (0|1): the fast match kernel normally tests 4 sampled rows of
      * every 32-row word and verifies the words that pass; 1 makes it evaluate all 32 cells

@@ -187,9 +187,7 @@ struct nb200_ctx {
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
     nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes, d_fp_wsplit;
-    nb200::DevBuf d_g4_twa, d_g4_twb, d_g4_base, d_g4_notes;
-    int k1_variant = 0;   // 0: default (= 16); 1: 64 values per lane; 8/10/12: 32 values per lane, half parked in shared memory; 16 (112): half parked in TMEM, 16 (12) warps
-                          // per SM; 4/5/6: four warps per frame, that many frames per CTA
+    int k1_variant = 0;   // NB200_OPT_K1_VARIANT (include/needle_b200.h)
     nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
 

@@ -24,6 +24,7 @@
 // hashes near quantiser thresholds.  log((1+a)/(1+b)) < t is evaluated as
 // (1+a) < e^t (1+b).
 #include <cmath>
+#include <type_traits>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -866,23 +867,44 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
             const f2 *wlo = s_window + 32 * half + lane;
             const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
             if (REV >= 2) {
-                // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that)
+                // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that).
+                // REV >= 3: the two samples of a complex value come straight out of the conversion unit's
+                // half-word selects -- an even frame (4-byte aligned) needs ONE word per value, an odd one
+                // the high half of one word and the low half of the next; no funnel shift either way.  The
+                // parity is warp-uniform (one frame per warp): two copies of this section, one branch.
+                // (A tensor-map copy cannot fix the alignment for us: its box coordinates must be 16-byte
+                // aligned in the inner dimension -- a misaligned start is an illegal instruction.)
+                auto layer1 = [&](auto odd_tag) {
+                    constexpr int ODD = decltype(odd_tag)::value;   // 0: funnel shift (REV 2), 1: even frame, 2: odd frame
 #pragma unroll
-                for (int n1 = 0; n1 < 8; n1++) {
-                    f2 sv[4], wv[4];
+                    for (int n1 = 0; n1 < 8; n1++) {
+                        f2 sv[4], wv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int j = n1 + 8 * i;
-                        const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
-                        sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
-                        wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                        for (int i = 0; i < 4; i++) {
+                            const int j = n1 + 8 * i;
+                            if (ODD == 1) {
+                                sv[i] = s16x2_to_float_xu(ph[64 * j]);
+                            } else if (ODD == 2) {
+                                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                                sv[i] = make_float2((float)(short)(w0 >> 16), (float)(short)(w1 & 0xffffu));
+                            } else {
+                                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                                sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
+                            }
+                            wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                        }
+                        const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
+                        const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
+                        v[n1] = d0;
+                        v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
+                        v[n1 + 8] = d2;
+                        v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
                     }
-                    const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
-                    const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
-                    v[n1] = d0;
-                    v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
-                    v[n1 + 8] = d2;
-                    v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
+                };
+                if (REV >= 3) {
+                    if (shift) layer1(std::integral_constant<int, 2>()); else layer1(std::integral_constant<int, 1>());
+                } else {
+                    layer1(std::integral_constant<int, 0>());
                 }
                 if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
                 fft32_tail(v);
@@ -1069,211 +1091,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
     }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, TM_COLS);
-}
-
-// ---------------------------------------------------------------------------
-// K1, four-warps-per-frame variant ("g4").  The warp-per-frame kernel above keeps
-// 64 complex values per lane: 255 registers, 8 warps per SM, and ptxas has no
-// room to overlap dependent packed ops (ncu: issue active 49 %, stall "wait" 1.0).
-// Here a frame belongs to a GROUP of 128 threads holding 16 complex values each
-// (~64 registers -> 32 warps per SM), 2048 = 16 x 16 x 8:
-//   n = 128 a + 8 b + c,  k = ka + 16 kb + 256 kc
-//   pass A  thread r = 8b+c: 16-point FFT over a, twiddle W_2048^(r ka)   -> E1[ka][r]
-//   pass B  thread (ka, c):  16-point FFT over b, twiddle W_128^(c kb)    -> E2[ka + 16 kb][c]
-//   pass C  thread j: residues q = j and 256 - j, 8-point FFT over c each -> Z[q + 256 kc]
-// The partner bin Z[2048 - k] of the split step has residue 256 - q: it is in
-// the SAME thread, so the split needs no exchange at all, and
-// |X[2048-k]|^2 = |E - W O|^2 comes for free next to |X[k]|^2 = |E + W O|^2.
-// Two transposes through shared memory (named barriers per group), chroma
-// fold by per-thread accumulators in shared memory.
-constexpr int G4_THREADS = 128;
-constexpr int G4_E1_STRIDE = 136;                 // float2 row stride of E1 (16 rows), conflict-free both ways
-constexpr int G4_E_ELEMS = 16 * G4_E1_STRIDE;     // 2176 >= 2048 (E2: 256 rows of 8, XOR-swizzled)
-constexpr int G4_TWB_STRIDE = 17;
-constexpr int g4_smem_bytes(int groups) { return (FP_HALF + 8 * G4_TWB_STRIDE + groups * G4_E_ELEMS) * 8; }
-
-__constant__ float2 c_w16[16], c_w16r[16];        // exp(-2 pi i e / 16) and its (-y, x) form
-
-// 16-point FFT, n = n1 + 4 n2, k = 4 k1 + k2: X[4 k1 + k2] ends up at v[k1 + 4 k2].
-__device__ __forceinline__ void fft16(f2 *v) {
-#pragma unroll
-    for (int n1 = 0; n1 < 4; n1++) fft4<4>(v + n1);
-#pragma unroll
-    for (int n1 = 1; n1 < 4; n1++)
-#pragma unroll
-        for (int k2 = 1; k2 < 4; k2++)
-            v[n1 + 4 * k2] = cmulc(v[n1 + 4 * k2], c_w16[n1 * k2], c_w16r[n1 * k2]);
-#pragma unroll
-    for (int k2 = 0; k2 < 4; k2++) fft4<1>(v + 4 * k2);
-}
-__device__ __forceinline__ constexpr int pos16(int k) { return (k >> 2) + 4 * (k & 3); }
-
-struct G4Args {
-    const int16_t *pcm;
-    const FpSegment *segs;
-    uint32_t n_segs;
-    uint32_t frame_begin, frame_end;
-    const float2 *window;    // [2048]
-    const float2 *tw_a;      // [16][128] W_2048^(r ka)
-    const float2 *tw_b;      // [8][17]   W_128^(c kb)
-    const float2 *base;      // [128][2]  W_4096^(q1), W_4096^(q2) of thread j
-    const uint2 *notes;      // [128]     11 x 4-bit pitch classes of thread j's bins (12 = unused)
-    float *chroma;
-};
-
-// E2[q][c] lives at 8 q + (c ^ ((q >> 1) & 7)): writers (two consecutive ka x eight c per
-// half-warp) and readers (sixteen consecutive q, one c) both hit 16 distinct 8-byte banks.
-__device__ __forceinline__ int e2_index(int q, int c) { return 8 * q + (c ^ ((q >> 1) & 7)); }
-
-__device__ __forceinline__ void group_sync(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G4_THREADS) : "memory");
-}
-
-__device__ __forceinline__ const int16_t *frame_src_g4(const G4Args &a, uint32_t frame) {
-    uint32_t lo = 0, hi = a.n_segs;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a.segs[mid].frame_begin <= frame) lo = mid; else hi = mid;
-    }
-    return a.pcm + a.segs[lo].pcm_off + (uint64_t)(frame - a.segs[lo].frame_begin) * FP_HOP;
-}
-
-__device__ __forceinline__ float power2(f2 x) { return fmaf(x.x, x.x, x.y * x.y); }
-
-// G4_GROUPS = frames in flight per CTA: 4 -> 128 registers per thread, 5 -> 102, 6 -> 85
-template <int G4_GROUPS>
-__global__ void __launch_bounds__(G4_GROUPS *G4_THREADS, 1) fp_fft_chroma_g4_kernel(const G4Args a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    f2 *s_window = reinterpret_cast<f2 *>(smem_raw);          // 2048
-    f2 *s_twb = s_window + FP_HALF;                           // 8 * 17
-    f2 *s_e_all = s_twb + 8 * G4_TWB_STRIDE;                  // G4_GROUPS * G4_E_ELEMS
-
-    for (int i = threadIdx.x; i < FP_HALF; i += blockDim.x) s_window[i] = a.window[i];
-    if (threadIdx.x < 8 * G4_TWB_STRIDE) s_twb[threadIdx.x] = a.tw_b[threadIdx.x];
-    __syncthreads();
-
-    const int group = threadIdx.x >> 7;
-    const int r = threadIdx.x & (G4_THREADS - 1);
-    const int lane = threadIdx.x & 31;
-    const int wig = r >> 5;                                   // warp in group
-    f2 *E = s_e_all + group * G4_E_ELEMS;
-    float *acc = reinterpret_cast<float *>(E);                // [13][128], aliases E between pass C and the next frame
-    const int ka_b = r >> 3, c_b = r & 7;                     // pass B role
-    const int q1 = r == 0 ? 0 : r, q2 = r == 0 ? 128 : 256 - r;   // pass C role
-    const f2 base1 = a.base[2 * r], base2 = a.base[2 * r + 1];
-    const uint2 notes = a.notes[r];
-    // pass-A twiddles W_2048^(r ka), ka = 1..15: thread constants, kept in registers for all frames
-    f2 twa[15];
-#pragma unroll
-    for (int ka = 1; ka < 16; ka++) twa[ka - 1] = a.tw_a[ka * G4_THREADS + r];
-
-    const uint32_t n_blocks = (a.frame_end - a.frame_begin + G4_GROUPS - 1) / G4_GROUPS;
-    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const uint32_t frame = a.frame_begin + blk * G4_GROUPS + group;
-        if (frame >= a.frame_end) break;                      // uniform per group; only group barriers below
-        const int16_t *src = frame_src_g4(a, frame);
-
-        f2 v[16];
-        // ---- pass A: z[128 a + r], window fused, 16-point FFT over a
-        if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + r;
-#pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = mul2(s16x2_to_float(__ldg(p + 128 * i)), s_window[128 * i + r]);
-        } else {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(src - 1) + r;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t w0 = __ldg(p + 128 * i), w1 = __ldg(p + 128 * i + 1);
-                v[i] = mul2(s16x2_to_float(__funnelshift_r(w0, w1, 16)), s_window[128 * i + r]);
-            }
-        }
-        fft16(v);
-        E[r] = v[0];
-#pragma unroll
-        for (int ka = 1; ka < 16; ka++) E[ka * G4_E1_STRIDE + r] = cmul(v[pos16(ka)], twa[ka - 1]);
-        group_sync(group);
-
-        // ---- pass B: thread (ka, c), 16-point FFT over b
-#pragma unroll
-        for (int b = 0; b < 16; b++) v[b] = E[ka_b * G4_E1_STRIDE + 8 * b + c_b];
-        group_sync(group);
-        fft16(v);
-        E[e2_index(ka_b, c_b)] = v[0];
-#pragma unroll
-        for (int kb = 1; kb < 16; kb++)
-            E[e2_index(ka_b + 16 * kb, c_b)] = cmul(v[pos16(kb)], s_twb[c_b * G4_TWB_STRIDE + kb]);
-        group_sync(group);
-
-        // ---- pass C: residues q1, q2 = 256 - q1 (thread 0: 0 and 128), 8-point FFT over c
-#pragma unroll
-        for (int c = 0; c < 8; c++) {
-            v[c] = E[e2_index(q1, c)];
-            v[8 + c] = E[e2_index(q2, c)];
-        }
-        group_sync(group);
-#pragma unroll
-        for (int n = 0; n < 13; n++) acc[n * G4_THREADS + r] = 0.f;
-        fft8<1>(v);
-        fft8<1>(v + 8);
-        // now Z[q1 + 256 kc] = v[kc], Z[q2 + 256 kc] = v[8 + kc]
-
-        // ---- split + power + chroma fold
-        if (r != 0) {
-            // k = q1 + 256 kc pairs with 2048 - k = q2 + 256 (7 - kc)
-#pragma unroll
-            for (int kc = 0; kc < 8; kc++) {
-                const f2 z = v[kc], zp = v[8 + 7 - kc];
-                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);               // 2E
-                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));     // 2O
-                const f2 w = cmulc(base1, c_w16[kc], c_w16r[kc]);               // W_4096^(q1 + 256 kc)
-                const f2 t = cmul(o, w);
-                if (kc <= 5) {                                                  // bin k: slot kc
-                    const uint32_t note = ((kc < 8 ? notes.x : notes.y) >> (4 * (kc & 7))) & 15u;
-                    acc[note * G4_THREADS + r] += power2(add2(e, t));
-                }
-                if (kc >= 3) {                                                  // bin 2048 - k: slot 6 + (kc - 3)
-                    const int s = 6 + kc - 3;
-                    const uint32_t note = ((s < 8 ? notes.x : notes.y) >> (4 * (s & 7))) & 15u;
-                    acc[note * G4_THREADS + r] += power2(sub2(e, t));
-                }
-            }
-        } else {
-            // residue 0: k = 256 kc pairs with 256 (8 - kc) inside v[0..8); slots 0..4 <-> kc = 1..5
-#pragma unroll
-            for (int kc = 1; kc <= 5; kc++) {
-                const f2 z = v[kc], zp = v[(8 - kc) & 7];
-                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
-                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
-                const f2 t = cmulc(o, c_w16[kc], c_w16r[kc]);                   // W_4096^(256 kc) = W_16^kc
-                const uint32_t note = (notes.x >> (4 * (kc - 1))) & 15u;
-                acc[note * G4_THREADS + r] += power2(add2(e, t));
-            }
-            // residue 128: k = 128 + 256 kc pairs with 128 + 256 (7 - kc) inside v[8..16); slots 5..9 <-> kc = 0..4
-#pragma unroll
-            for (int kc = 0; kc <= 4; kc++) {
-                const f2 z = v[8 + kc], zp = v[8 + 7 - kc];
-                const f2 e = fma2(zp, make_float2(1.f, -1.f), z);
-                const f2 o = fma2(swp(z), make_float2(1.f, -1.f), swp(zp));
-                const f2 w = cmulc(base2, c_w16[kc], c_w16r[kc]);               // W_4096^(128 + 256 kc)
-                const f2 t = cmul(o, w);
-                const int s = 5 + kc;
-                const uint32_t note = ((s < 8 ? notes.x : notes.y) >> (4 * (s & 7))) & 15u;
-                acc[note * G4_THREADS + r] += power2(add2(e, t));
-            }
-        }
-        group_sync(group);
-        // ---- reduce: warp w of the group sums pitch classes 3w .. 3w+2 over the 128 threads
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const int n = 3 * wig + i;
-            float s = (acc[n * G4_THREADS + lane] + acc[n * G4_THREADS + 32 + lane]) +
-                      (acc[n * G4_THREADS + 64 + lane] + acc[n * G4_THREADS + 96 + lane]);
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) a.chroma[(uint64_t)frame * FP_BANDS + n] = 0.25f * s;
-        }
-        group_sync(group);   // acc is about to be overwritten by the next frame's E1
-    }
 }
 
 // --------------------------------------------------------------------- K2
@@ -1490,65 +1307,6 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpyToSymbol(c_w64r, rot(w64).data(), sizeof(float2) * 64));
     NB_CUDA(cudaMemcpyToSymbol(c_w32r, rot(w32).data(), sizeof(float2) * 32));
     NB_CUDA(cudaMemcpyToSymbol(c_w128r, rot(w128).data(), sizeof(float2) * FP_T));
-    {
-        std::vector<float2> w16(16);
-        for (int e = 0; e < 16; e++) w16[e] = make_float2((float)cos(-2.0 * PI * e / 16), (float)sin(-2.0 * PI * e / 16));
-        NB_CUDA(cudaMemcpyToSymbol(c_w16, w16.data(), sizeof(float2) * 16));
-        NB_CUDA(cudaMemcpyToSymbol(c_w16r, rot(w16).data(), sizeof(float2) * 16));
-    }
-    {
-        // tables of the four-warps-per-frame kernel
-        std::vector<float2> twa(16 * G4_THREADS), twb(8 * G4_TWB_STRIDE, make_float2(1.f, 0.f)), base(2 * G4_THREADS);
-        std::vector<uint2> notes4(G4_THREADS);
-        for (int ka = 0; ka < 16; ka++)
-            for (int r = 0; r < G4_THREADS; r++) {
-                const double ang = -2.0 * PI * (double)(r * ka) / FP_HALF;
-                twa[ka * G4_THREADS + r] = make_float2((float)cos(ang), (float)sin(ang));
-            }
-        for (int c = 0; c < 8; c++)
-            for (int kb = 0; kb < 16; kb++) {
-                const double ang = -2.0 * PI * (double)(c * kb) / 128.0;
-                twb[c * G4_TWB_STRIDE + kb] = make_float2((float)cos(ang), (float)sin(ang));
-            }
-        auto note_of = [&](int k) -> uint32_t {
-            if (k < min_index || k >= max_index) return 12u;
-            const double freq = (double)k * FP_SAMPLE_RATE / FP_FRAME;
-            const double octave = log(freq / (440.0 / 16.0)) / log(2.0);
-            return (uint32_t)(int)(FP_BANDS * (octave - floor(octave)));
-        };
-        for (int j = 0; j < G4_THREADS; j++) {
-            const int q1 = j == 0 ? 0 : j, q2 = j == 0 ? 128 : 256 - j;
-            base[2 * j] = make_float2((float)cos(-2.0 * PI * q1 / FP_FRAME), (float)sin(-2.0 * PI * q1 / FP_FRAME));
-            base[2 * j + 1] = make_float2((float)cos(-2.0 * PI * q2 / FP_FRAME), (float)sin(-2.0 * PI * q2 / FP_FRAME));
-            uint64_t bits = 0;
-            for (int s2 = 0; s2 < 16; s2++) {
-                int k = -1;
-                if (j != 0) {
-                    if (s2 <= 5) k = q1 + 256 * s2;                       // bin k, kc = s2
-                    else if (s2 <= 10) k = FP_HALF - (q1 + 256 * (s2 - 3));   // bin 2048 - k, kc = s2 - 3
-                } else {
-                    if (s2 <= 4) k = 256 * (s2 + 1);                      // residue 0, kc = s2 + 1
-                    else if (s2 <= 9) k = 128 + 256 * (s2 - 5);           // residue 128, kc = s2 - 5
-                }
-                bits |= (uint64_t)(k < 0 ? 12u : note_of(k)) << (4 * s2);
-            }
-            notes4[j] = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
-        }
-        NB_TRY(ctx->d_g4_twa.alloc(sizeof(float2) * twa.size()));
-        NB_TRY(ctx->d_g4_twb.alloc(sizeof(float2) * twb.size()));
-        NB_TRY(ctx->d_g4_base.alloc(sizeof(float2) * base.size()));
-        NB_TRY(ctx->d_g4_notes.alloc(sizeof(uint2) * notes4.size()));
-        NB_CUDA(cudaMemcpy(ctx->d_g4_twa.p, twa.data(), sizeof(float2) * twa.size(), cudaMemcpyHostToDevice));
-        NB_CUDA(cudaMemcpy(ctx->d_g4_twb.p, twb.data(), sizeof(float2) * twb.size(), cudaMemcpyHostToDevice));
-        NB_CUDA(cudaMemcpy(ctx->d_g4_base.p, base.data(), sizeof(float2) * base.size(), cudaMemcpyHostToDevice));
-        NB_CUDA(cudaMemcpy(ctx->d_g4_notes.p, notes4.data(), sizeof(uint2) * notes4.size(), cudaMemcpyHostToDevice));
-        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     g4_smem_bytes(4)));
-        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     g4_smem_bytes(5)));
-        NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_g4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     g4_smem_bytes(6)));
-    }
     NB_CUDA(cudaMemcpyToSymbol(c_cls, cls, sizeof(cls)));
     NB_CUDA(cudaMemcpyToSymbol(c_fir, FP_FIR_COEFFS, sizeof(double) * FP_FIR_LEN));
     NB_TRY(ctx->d_fp_window.alloc(sizeof(float2) * FP_HALF));
@@ -1570,6 +1328,8 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<16>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<12>()));
@@ -1678,16 +1438,6 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         k1.lane_w = ctx->d_fp_lane.as<float2>();
         k1.wsplit = ctx->d_fp_wsplit.as<float2>();
         k1.chroma = ctx->d_chroma.as<float>();
-        G4Args g;
-        g.pcm = k1.pcm;
-        g.segs = k1.segs;
-        g.n_segs = nseg;
-        g.window = k1.window;
-        g.tw_a = ctx->d_g4_twa.as<float2>();
-        g.tw_b = ctx->d_g4_twb.as<float2>();
-        g.base = ctx->d_g4_base.as<float2>();
-        g.notes = ctx->d_g4_notes.as<uint2>();
-        g.chroma = k1.chroma;
         // K1 over global frames [f0, f1)
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
@@ -1699,7 +1449,9 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
                 k1.frame_end = f1;
                 const uint32_t nw = variant == 112 ? 12u : 16u;
                 const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
-                if (variant == 17)
+                if (variant == 18)
+                    fp_fft_chroma_tm_kernel<16, 3><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                else if (variant == 17)
                     fp_fft_chroma_tm_kernel<16, 2><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
                 else if (nw == 16)
                     fp_fft_chroma_tm_kernel<16, 1><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
@@ -1716,17 +1468,6 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
                     fp_fft_chroma_h32_kernel<10><<<grid1, 10 * 32, h32_smem_bytes<10>(), st>>>(k1);
                 else
                     fp_fft_chroma_h32_kernel<8><<<grid1, 8 * 32, h32_smem_bytes<8>(), st>>>(k1);
-            } else if (variant >= 4) {
-                const int groups = variant;
-                g.frame_begin = f0;
-                g.frame_end = f1;
-                const uint32_t ggrid = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + groups - 1) / groups);
-                if (groups == 4)
-                    fp_fft_chroma_g4_kernel<4><<<ggrid, 4 * G4_THREADS, g4_smem_bytes(4), st>>>(g);
-                else if (groups == 5)
-                    fp_fft_chroma_g4_kernel<5><<<ggrid, 5 * G4_THREADS, g4_smem_bytes(5), st>>>(g);
-                else
-                    fp_fft_chroma_g4_kernel<6><<<ggrid, 6 * G4_THREADS, g4_smem_bytes(6), st>>>(g);
             } else {
                 k1.frame_begin = f0;
                 k1.frame_end = f1;

@@ -32,11 +32,11 @@ def make_pcm(seed, seconds, kind="mix"):
     return np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 4, 5, 6, 8, 10])
+@pytest.mark.parametrize("variant", [0, 1, 8, 12, 16, 112])
 @pytest.mark.parametrize("kind", ["noise", "chords", "mix"])
 def test_raw_hashes_match_oracle(ctx, oracle, kind, variant):
-    """Every K1 kernel variant (0 = 12: one warp per frame, 32 values per lane, 12 warps per SM; 8/10:
-    the same with fewer warps; 1: 64 values per lane; 4/5/6: four warps per frame)."""
+    """Every K1 kernel variant (NB200_OPT_K1_VARIANT: 0 = the default tensor-memory kernel; 16/112 its
+    first arithmetic revision with 16/12 warps; 8/12: parked half in shared memory; 1: 64 values per lane)."""
     from needle_b200._lib import OPT_K1_VARIANT
     pcm = make_pcm(1, 120.0, kind)
     want = oracle.fingerprint(pcm)
