@@ -24,7 +24,6 @@
 // hashes near quantiser thresholds.  log((1+a)/(1+b)) < t is evaluated as
 // (1+a) < e^t (1+b).
 #include <cmath>
-#include <type_traits>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -867,44 +866,24 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
             const f2 *wlo = s_window + 32 * half + lane;
             const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
             if (REV >= 2) {
-                // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that).
-                // REV >= 3: the two samples of a complex value come straight out of the conversion unit's
-                // half-word selects -- an even frame (4-byte aligned) needs ONE word per value, an odd one
-                // the high half of one word and the low half of the next; no funnel shift either way.  The
-                // parity is warp-uniform (one frame per warp): two copies of this section, one branch.
-                // (A tensor-map copy cannot fix the alignment for us: its box coordinates must be 16-byte
-                // aligned in the inner dimension -- a misaligned start is an illegal instruction.)
-                auto layer1 = [&](auto odd_tag) {
-                    constexpr int ODD = decltype(odd_tag)::value;   // 0: funnel shift (REV 2), 1: even frame, 2: odd frame
+                // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that);
+                // the samples go through the conversion unit (I2F.S16 on each half of the word)
 #pragma unroll
-                    for (int n1 = 0; n1 < 8; n1++) {
-                        f2 sv[4], wv[4];
+                for (int n1 = 0; n1 < 8; n1++) {
+                    f2 sv[4], wv[4];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const int j = n1 + 8 * i;
-                            if (ODD == 1) {
-                                sv[i] = s16x2_to_float_xu(ph[64 * j]);
-                            } else if (ODD == 2) {
-                                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
-                                sv[i] = make_float2((float)(short)(w0 >> 16), (float)(short)(w1 & 0xffffu));
-                            } else {
-                                const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
-                                sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
-                            }
-                            wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
-                        }
-                        const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
-                        const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
-                        v[n1] = d0;
-                        v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
-                        v[n1 + 8] = d2;
-                        v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
+                    for (int i = 0; i < 4; i++) {
+                        const int j = n1 + 8 * i;
+                        const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                        sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
+                        wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
                     }
-                };
-                if (REV >= 3) {
-                    if (shift) layer1(std::integral_constant<int, 2>()); else layer1(std::integral_constant<int, 1>());
-                } else {
-                    layer1(std::integral_constant<int, 0>());
+                    const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
+                    const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
+                    v[n1] = d0;
+                    v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
+                    v[n1 + 8] = d2;
+                    v[n1 + 24] = fma2(c1, make_float2(2.f, 2.f), neg2(d2));
                 }
                 if (half == 1) __syncwarp();   // every lane has taken its PCM: the rows may be overwritten
                 fft32_tail(v);
@@ -1329,8 +1308,6 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
-    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<12>()));
     ctx->fp_ready = true;
@@ -1449,9 +1426,7 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
                 k1.frame_end = f1;
                 const uint32_t nw = variant == 112 ? 12u : 16u;
                 const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
-                if (variant == 18)
-                    fp_fft_chroma_tm_kernel<16, 3><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
-                else if (variant == 17)
+                if (variant == 17)
                     fp_fft_chroma_tm_kernel<16, 2><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
                 else if (nw == 16)
                     fp_fft_chroma_tm_kernel<16, 1><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);

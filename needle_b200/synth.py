@@ -215,3 +215,44 @@ def make_hash_season(n_videos: int, n_open: int, n_end: int, seed: int = 0, run_
             off.append(off[-1] + n)
     return HashSeason(np.concatenate(hs), np.concatenate(ts), np.asarray(off, dtype=np.uint64),
                       np.full(n_videos, HASH_DURATION_NS, dtype=np.uint64))
+
+
+SILENCE_HASH = 627964279   # Chromaprint TEST2 sub-fingerprint of digital silence (upstream tests/test_api.cpp)
+
+
+def make_adversarial_season(kind: str, n_videos: int, n_open: int, n_end: int, seed: int = 7) -> HashSeason:
+    """Seasons built to keep diagonals of the match matrix alive (what real TV audio does and uniform
+    random hashes do not): `random` (the planted-run season), `correlated` (each hash = the previous
+    with 3 bit flips), `silence60` (60 s of one constant hash somewhere in every list: a block of
+    matching cells in every table), `jingle20` (a 40-hash jingle repeated 20 times in every list:
+    thousands of runs below the 20 s minimum), `quiet_half` (the second half of every list silent),
+    `all_silence` (every hash identical: every cell with i, j >= 1 matches)."""
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        return make_hash_season(n_videos, n_open, n_end, seed=seed)
+    if kind == "correlated":
+        return make_hash_season(n_videos, n_open, n_end, seed=seed, correlated=True)
+    s = make_hash_season(n_videos, n_open, n_end, seed=seed)
+    off = s.seg_offset.astype(np.int64)
+    jingle = rng.integers(0, 2 ** 32, 40, dtype=np.uint64).astype(np.uint32)
+    for k in range(2 * n_videos):
+        a, b = int(off[k]), int(off[k + 1])
+        ln = b - a
+        if ln < 4:
+            continue
+        if kind == "silence60":
+            w = min(244, ln - 2)
+            at = int(rng.integers(1, ln - w + 1))
+            s.hashes[a + at:a + at + w] = SILENCE_HASH
+        elif kind == "jingle20":
+            if ln > 48:
+                for _ in range(20):
+                    at = int(rng.integers(1, ln - 41))
+                    s.hashes[a + at:a + at + 40] = jingle
+        elif kind == "quiet_half":
+            s.hashes[a + ln // 2:b] = SILENCE_HASH
+        elif kind == "all_silence":
+            s.hashes[a:b] = SILENCE_HASH
+        else:
+            raise ValueError(kind)
+    return s

@@ -255,6 +255,25 @@ def test_time_padding_and_hash_durations(ctx, oracle):
     check_season(ctx, oracle, season, include_endings=True, time_padding_ns=1_500_000_000)
 
 
+@pytest.mark.parametrize("kind", ["correlated", "silence60", "jingle20", "quiet_half", "all_silence"])
+def test_adversarial_seasons_equal_oracle(ctx, oracle, kind):
+    """Seasons that keep diagonals alive (silence = one constant hash, repeated jingles, correlated
+    background): every kernel's run list against the oracle, bit for bit.  The vote is skipped where
+    the candidate count makes find_best_match quadratic in tens of thousands (in the reference too)."""
+    season = synth.make_adversarial_season(kind, 4, 700, 400, seed=5)
+    vote = kind in ("correlated", "jingle20")
+    runs, _ = check_season(ctx, oracle, season, vote=vote, include_endings=True)
+    if kind in ("silence60", "quiet_half", "all_silence"):
+        assert len(runs) > 100      # blocks of matching cells: many qualifying diagonals
+
+
+def test_adversarial_silence_short_minimum(ctx, oracle):
+    """The same with a 2 s minimum (general kernel: candidate runs shorter than 63 cells)."""
+    season = synth.make_adversarial_season("silence60", 3, 400, 300, seed=6)
+    check_season(ctx, oracle, season, vote=False, include_endings=True, min_opening_ns=2_000_000_000,
+                 min_ending_ns=2_000_000_000)
+
+
 def test_full_size_24min_season(ctx, oracle):
     """BASELINE config sizes (24-min episodes: 2897 / 1443 hashes), 6 videos."""
     season = synth.make_hash_season(6, 2897, 1443, seed=24)
