@@ -61,6 +61,15 @@ class PathNotFound(NeedleError):
     pass
 
 
+def json_f32(x) -> str:
+    """serde_json's rendering of an f32 (ryu): the shortest decimal that round-trips, always with a
+    fraction or an exponent; exponents without padding (1e-5, 1e16)."""
+    v = np.float32(x)
+    s = np.format_float_positional(v, unique=True, trim="0") if (v == 0 or 1e-5 <= abs(float(v)) < 1e16) else \
+        np.format_float_scientific(v, unique=True, trim="-", exp_digits=1).replace("e+", "e")
+    return s
+
+
 class ComparatorMinimumPaths(NeedleError):
     pass
 
@@ -408,8 +417,10 @@ class Comparator:
         if opening is None and ending is None:
             return
         md5 = compute_header_md5sum(video)
+        # the bytes serde_json writes (comparator.rs:329-354): f32 values in their shortest form
+        pair = lambda r: "null" if r is None else "[%s,%s]" % (json_f32(r[0]), json_f32(r[1]))
         with open(_with_extension(video, SKIP_FILE_NAME), "w") as f:
-            json.dump({"opening": opening, "ending": ending, "md5": md5}, f, separators=(",", ":"))
+            f.write('{"opening":%s,"ending":%s,"md5":"%s"}' % (pair(opening), pair(ending), md5))
 
     def display_opening_ending_info(self, r: SearchResult):
         if r.opening is not None:

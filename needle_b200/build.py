@@ -20,7 +20,8 @@ CAPI_LIB = os.path.join(HERE, "libneedle.so")   # the needle-capi ABI (include/n
 OBJ_DIR = os.path.join(HERE, "_obj")
 
 SOURCES = ["api.cu", "match.cu", "fingerprint.cu", "vote_device.cu", "multi.cu", "vote.cpp", "persist.cpp"]
-HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"),
+HEADERS = [os.path.join(CSRC, "common.h"), os.path.join(CSRC, "fp_tables.h"), os.path.join(CSRC, "tma.cuh"),
+           os.path.join(CSRC, "fp_chroma_fold.inc"),
            os.path.join(INCLUDE, "needle_b200.h"), os.path.join(INCLUDE, "needle.h")]
 
 NVCC_FLAGS = [

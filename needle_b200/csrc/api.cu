@@ -295,6 +295,13 @@ int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t 
         delete hs;
         return NB200_ERR_CUDA;
     }
+    // h_stage also carries the match stage's descriptor tables: an unsynchronised nb200_match_export
+    // (or a deferred-wait job) may still be copying them from here on the copy stream
+    if (cudaEventSynchronize(ctx->ev_chunk[8]) != cudaSuccess || cudaEventSynchronize(ctx->ev_chunk[10]) != cudaSuccess) {
+        set_last_error("cudaEventSynchronize(match staging)", cudaGetLastError());
+        delete hs;
+        return NB200_ERR_CUDA;
+    }
     uint64_t *st_t = ctx->h_stage.as<uint64_t>();
     uint32_t *st_h = reinterpret_cast<uint32_t *>(st_t + hs->dev_total);
     memset(ctx->h_stage.p, 0, b_h + b_t);

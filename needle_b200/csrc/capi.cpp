@@ -333,6 +333,18 @@ std::string json_f32(float x) {
     char buf[64];
     auto r = std::to_chars(buf, buf + sizeof(buf), x);
     std::string s(buf, r.ptr);
+    // ryu (what serde_json prints with) writes exponents without sign padding: 1e-5, 1e16
+    const size_t e = s.find('e');
+    if (e != std::string::npos) {
+        size_t k = e + 1;
+        std::string sign;
+        if (k < s.size() && (s[k] == '+' || s[k] == '-')) {
+            if (s[k] == '-') sign = "-";
+            k++;
+        }
+        while (k + 1 < s.size() && s[k] == '0') k++;
+        s = s.substr(0, e + 1) + sign + s.substr(k);
+    }
     if (s.find_first_of(".eE") == std::string::npos) s += ".0";
     return s;
 }

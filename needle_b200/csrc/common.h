@@ -174,7 +174,7 @@ struct nb200_ctx {
     bool defer_wait = false;            // *_into fingerprint calls return without waiting for the stream
     bool host_vote = false;             // searches download the runs and vote on the host (vote.cpp) instead of on the device
     nb200::DevBuf d_problems;   // the match stage's descriptor arena: segment table, run-length bounds, both tilings
-    nb200::DevBuf d_counters, d_runs;
+    nb200::DevBuf d_counters, d_runs, d_dst2;   // d_dst2: the fast match kernel's repeated dst lists
     nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
     nb200::PinnedBuf h_fp_stage, h_vote_stage, h_results;   // one staging area per phase: nothing waits for a copy to drain
     // device vote scratch (vote_device.cu)

@@ -30,6 +30,7 @@
 
 #include "common.h"
 #include "fp_tables.h"
+#include "tma.cuh"
 
 namespace nb200 {
 
@@ -173,36 +174,13 @@ __device__ __forceinline__ f2 s16x2_to_float_xu(uint32_t w) {
     return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
 }
 
-// ---- 1-D bulk async copy (TMA) + mbarrier, shared::cta addresses as u32
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "NB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra NB_DONE_%=;\n"
-        "bra NB_WAIT_%=;\n"
-        "NB_DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
+// (1-D bulk async copy + mbarrier helpers: tma.cuh)
 // float2 store to shared memory as ONE st.shared.v2.f32 whose operands are the value's own
 // registers.  The C++ form (`buf[i] = packed_result`) makes ptxas copy every result into a
 // staging register pair first: two MOVs per store, ~17 % of this kernel's instructions.
 __device__ __forceinline__ void sts2(uint32_t addr, float2 v) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct FpSegment {
     uint64_t pcm_off;      // element offset of the segment's mono PCM
@@ -1858,7 +1836,11 @@ int nb200_analyze_search(nb200_ctx *ctx, const int16_t *const *pcm, const uint64
     if (channels == 1) {
         // mono: stream the PCM in chunk by chunk underneath K1
         NB_TRY(pcmset_make(ctx, pcm, n_samples_total, channels, 2 * n_videos, false, &ps));
-        NB_TRY(ensure_fp_tables(ctx));
+        st = ensure_fp_tables(ctx);
+        if (st != NB200_OK) {
+            nb200_pcmset_free(ps);
+            return st;
+        }
         st = fingerprint_run_pipelined(ctx, ps, pcm, (uint32_t)stride, NB200_DELAY_MS * 1000000ull,
                                        NB200_ITEM_DURATION_MS * 1000000ull, seek_to_ns, &hs, nullptr, nullptr, 0,
                                        /*wait=*/false);

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "common.h"
+#include "tma.cuh"
 
 namespace nb200 {
 
@@ -58,6 +59,9 @@ struct MatchProblem {
     uint32_t tile_begin;    // first global tile id
     uint32_t group;         // 2 * (global pair index) + is_ending
     uint32_t src_seg, dst_seg;   // segment indices (2 * video + is_ending): where lcand comes from
+    // fast kernel: the dst list's live columns 1 .. m-1, padded to `period` (a multiple of 4) and
+    // repeated, so that every wrapped 512-column window is ONE 16-byte-aligned span (dst2_build_kernel)
+    uint32_t dst2_off, period;
 };
 
 struct MatchArgs {
@@ -66,6 +70,7 @@ struct MatchArgs {
     const MatchProblem *problems;
     const uint32_t *tile_end;   // [n_problems] exclusive end tile id per problem
     const uint32_t *lut;        // [n_tiles >> LUT_SHIFT + 1] first problem whose tile_end > (k << LUT_SHIFT)
+    const uint32_t *dst2;       // fast kernel: repeated live columns of every list (MatchProblem::dst2_off)
     uint32_t n_tiles;
     uint32_t threshold;
     uint32_t run_cap;
@@ -180,8 +185,8 @@ __device__ __noinline__ void walk_and_emit(const EmitCtx a, uint32_t problem, in
 }
 
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchArgs a) {
-    __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][SRC_TILE];
-    __shared__ __align__(16) uint32_t s_dst[MATCH_WARPS][DST_TILE];
+    __shared__ __align__(128) uint32_t s_src[MATCH_WARPS][SRC_TILE];
+    __shared__ __align__(128) uint32_t s_dst[MATCH_WARPS][DST_TILE];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -191,6 +196,14 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchA
     const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
     const int ybias = -(int)(T + 1);    // popc + ybias < 0  <=>  popc <= T
     if (not_my_turn(a)) return;
+    __shared__ __align__(8) uint64_t s_bar[MATCH_WARPS];
+    const uint32_t bar = smem_u32(&s_bar[warp]);
+    uint32_t phase = 0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
     for (;;) {
         uint32_t tile = 0;
@@ -214,19 +227,27 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchA
         const int tile_j0 = r0 - dband - (MATCH_DW + 3);   // dst_t[s] = dst[tile_j0 + s]
         const int tile_i0 = r0 - 4;                        // src_t[s] = src[tile_i0 + s]
 
-        // ---- stage the hash tiles (out-of-range entries are never used unmasked)
+        // ---- stage the hash tiles with 1-D bulk copies (TMA): both tiles are contiguous, 16-byte
+        //      aligned spans of the lists (tile_i0 and tile_j0 are multiples of 4).  Only the part that
+        //      lies inside the list is fetched -- out-of-range entries are never used unmasked -- and
+        //      its last 1..3 elements (a list need not end on a 16-byte boundary) by plain loads.
         __syncwarp();
         {
             const uint32_t *hs = a.hashes + pr.src_off;
             const uint32_t *hd = a.hashes + pr.dst_off;
-            for (int s = lane; s < SRC_TILE; s += 32) {
-                int i = tile_i0 + s;
-                src_t[s] = (i >= 0 && i < n) ? hs[i] : 0u;
+            const int si0 = max(tile_i0, 0), si1 = min(tile_i0 + SRC_TILE, n);
+            const int sj0 = max(tile_j0, 0), sj1 = min(tile_j0 + DST_TILE, m);
+            const int sn = max(si1 - si0, 0) & ~3, dn = max(sj1 - sj0, 0) & ~3;
+            fence_proxy_async();
+            if (lane == 0) {
+                mbar_expect_tx(bar, (uint32_t)(sn + dn) * 4u);
+                if (sn) bulk_g2s(smem_u32(src_t + (si0 - tile_i0)), hs + si0, (uint32_t)sn * 4u, bar);
+                if (dn) bulk_g2s(smem_u32(dst_t + (sj0 - tile_j0)), hd + sj0, (uint32_t)dn * 4u, bar);
             }
-            for (int s = lane; s < DST_TILE; s += 32) {
-                int j = tile_j0 + s;
-                dst_t[s] = (j >= 0 && j < m) ? hd[j] : 0u;
-            }
+            if (lane < 3 && si0 + sn + lane < si1) src_t[si0 + sn + lane - tile_i0] = hs[si0 + sn + lane];
+            if (lane >= 4 && lane < 7 && sj0 + dn + lane - 4 < sj1) dst_t[sj0 + dn + lane - 4 - tile_j0] = hd[sj0 + dn + lane - 4];
+            mbar_wait(bar, phase);
+            phase ^= 1;
         }
         __syncwarp();
 
@@ -398,11 +419,11 @@ __device__ __noinline__ void coop_long_run(const EmitCtx a, uint32_t problem, in
 
 // A full word (32 matching cells of wrapped diagonal u = ub + x starting at row i0) was found:
 // drop the look-alikes the wrapped tiling can produce, then let the warp walk the run.
-__device__ __forceinline__ void full_word(const EmitCtx &ectx, uint32_t p, int i0, int u, int M, int n, int lane) {
-    if (u >= M || i0 == 0 || i0 + 31 > n - 1) return;     // duplicate diagonal / row 0 / past the end
-    int jm = (i0 - 1 - u) % M;                              // j0 - 1
-    if (jm < 0) jm += M;
-    if (jm + 31 > M - 1) return;                            // the wrap point is inside the word
+__device__ __forceinline__ void full_word(const EmitCtx &ectx, uint32_t p, int i0, int u, int Mp, int M, int n, int lane) {
+    if (u >= Mp || i0 == 0 || i0 + 31 > n - 1) return;    // duplicate diagonal / row 0 / past the end
+    int jm = (i0 - 1 - u) % Mp;                             // j0 - 1
+    if (jm < 0) jm += Mp;
+    if (jm + 31 > M - 1) return;                            // the wrap point or a padding column is inside the word
     coop_long_run(ectx, p, i0, i0 - (jm + 1), lane);
 }
 
@@ -417,8 +438,8 @@ __device__ __forceinline__ void full_word(const EmitCtx &ectx, uint32_t p, int i
 // (load, XOR, POPC, vote), so it only pays for a handful: with 16 lanes alive it loses to
 // another stage.
 __device__ __noinline__ void coop_verify(const EmitCtx ectx, uint32_t p, const uint32_t *src_t, const uint32_t *dst_t,
-                                         int step, int i0, int ub, int M, int n, uint32_t lanes_alive, uint32_t mine,
-                                         int lane) {
+                                         int step, int i0, int ub, int Mp, int M, int n, uint32_t lanes_alive,
+                                         uint32_t mine, int lane) {
     const uint32_t sv = src_t[32 * step + lane];
     while (lanes_alive) {
         const int sl = __ffs((int)lanes_alive) - 1;
@@ -430,7 +451,7 @@ __device__ __noinline__ void coop_verify(const EmitCtx ectx, uint32_t p, const u
             const int x = sl * MATCH_C + c;
             // cell (row 32 step + lane, diagonal x) <-> dst_t[255 + 32 step + lane - x]
             const bool ok = __popc(sv ^ dst_t[255 + 32 * step + lane - x]) <= (int)ectx.threshold;
-            if (__all_sync(0xffffffffu, ok)) full_word(ectx, p, i0, ub + x, M, n, lane);
+            if (__all_sync(0xffffffffu, ok)) full_word(ectx, p, i0, ub + x, Mp, M, n, lane);
         }
     }
 }
@@ -452,53 +473,80 @@ __device__ __noinline__ void coop_verify(const EmitCtx ectx, uint32_t p, const u
 // POPCs.  Survivors of all 8 stages are exactly the full words.  Same runs, bit for bit.
 template <bool SAMPLED>
 __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const MatchArgs a) {
-    __shared__ __align__(16) uint32_t s_src[MATCH_WARPS][MATCH_R];
-    __shared__ __align__(16) uint32_t s_dst[MATCH_WARPS][FAST_DST_TILE];
+    // two tile buffers per warp: the next tile's hashes arrive by bulk copy (TMA) while this one is matched
+    __shared__ __align__(128) uint32_t s_src[MATCH_WARPS][2][MATCH_R];
+    __shared__ __align__(128) uint32_t s_dst[MATCH_WARPS][2][FAST_DST_TILE];
+    __shared__ __align__(8) uint64_t s_bar[MATCH_WARPS][2];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint32_t *src_t = s_src[warp];
-    uint32_t *dst_t = s_dst[warp];
     const int T = (int)a.threshold;
     const EmitCtx ectx = {a.hashes, a.ts, a.problems, a.counters, a.runs, a.run_cap, a.threshold};
     if (not_my_turn(a)) return;
+    if (lane == 0) {
+        mbar_init(smem_u32(&s_bar[warp][0]), 1);
+        mbar_init(smem_u32(&s_bar[warp][1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
 
-    for (;;) {
+    // Geometry of a tile: diagonals wrapped modulo the PERIOD Mp = (m - 1) rounded up to a multiple of 4;
+    // the dst window of a tile then starts at a multiple of 4 elements (r0, ub and 256 are), i.e. 16-byte
+    // aligned in the repeated list a.dst2 -- one bulk copy.  Columns M .. Mp-1 are padding: a word that
+    // touches them is rejected where full words are reported, like the wrap point.
+    struct Tile {
+        uint32_t p;
+        int n, M, Mp, r0, ub;
+    };
+    auto claim = [&](Tile &t) -> bool {   // next tile from the global cursor + its bulk copies into buffer b
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.n_tiles) break;
-
+        if (tile >= a.n_tiles) return false;
         uint32_t p = a.lut[tile >> LUT_SHIFT];
         while (tile >= a.tile_end[p]) p++;
-        const MatchProblem pr = a.problems[p];
-        const int n = (int)pr.n, M = (int)pr.m - 1;   // M live columns
+        const MatchProblem &pr = a.problems[p];
         const uint32_t local = tile - pr.tile_begin;
         const int chunk = (int)(local / pr.n_bands);
-        const int band = (int)(local - (uint32_t)chunk * pr.n_bands);
-        const int r0 = chunk * MATCH_R;
-        const int ub = band * MATCH_DW;
-        // dst_t[s] = dst[1 + ((e0 + s) mod M)],  cell (row r0+kk, diagonal ub+x) <-> s = 255 + kk - x
-        int e0 = (r0 - 1 - (ub + MATCH_DW - 1)) % M;
-        if (e0 < 0) e0 += M;
-
-        __syncwarp();
-        {
-            const uint32_t *hs = a.hashes + pr.src_off;
-            const uint32_t *hd = a.hashes + pr.dst_off + 1;
-            for (int s = lane; s < MATCH_R; s += 32) {
-                const int i = r0 + s;
-                src_t[s] = i < n ? hs[i] : 0u;
-            }
-            int idx = (e0 + lane) % M;
-            const int inc = 32 % M;
-            for (int s = lane; s < FAST_DST_TILE; s += 32) {
-                dst_t[s] = hd[idx];
-                idx += inc;
-                if (idx >= M) idx -= M;
-            }
+        t.p = p;
+        t.n = (int)pr.n;
+        t.M = (int)pr.m - 1;
+        t.Mp = (int)pr.period;
+        t.r0 = chunk * MATCH_R;
+        t.ub = (int)(local - (uint32_t)chunk * pr.n_bands) * MATCH_DW;
+        return true;
+    };
+    auto fetch = [&](const Tile &t, int b) {
+        const MatchProblem &pr = a.problems[t.p];
+        // dst_t[s] = column 1 + ((e0 + s) mod Mp) of dst,  cell (row r0+kk, diagonal ub+x) <-> s = 255 + kk - x
+        int e0 = (t.r0 - t.ub - MATCH_DW) % t.Mp;
+        if (e0 < 0) e0 += t.Mp;
+        const uint32_t *hs = a.hashes + pr.src_off + t.r0;
+        const int rows = min(MATCH_R, t.n - t.r0), sn = rows & ~3;   // rows past n are never used unmasked
+        fence_proxy_async();
+        if (lane == 0) {
+            const uint32_t bar = smem_u32(&s_bar[warp][b]);
+            mbar_expect_tx(bar, (uint32_t)sn * 4u + FAST_DST_TILE * 4u);
+            if (sn) bulk_g2s(smem_u32(&s_src[warp][b][0]), hs, (uint32_t)sn * 4u, bar);
+            bulk_g2s(smem_u32(&s_dst[warp][b][0]), a.dst2 + pr.dst2_off + e0, FAST_DST_TILE * 4u, bar);
         }
+        if (lane < 3 && sn + lane < rows) s_src[warp][b][sn + lane] = hs[sn + lane];   // a list need not end on 16 bytes
+    };
+
+    Tile cur, nxt;
+    bool have = claim(cur);
+    if (have) fetch(cur, 0);
+    uint32_t phase[2] = {0u, 0u};
+    for (int buf = 0; have; buf ^= 1) {
+        const bool have_next = claim(nxt);
+        if (have_next) fetch(nxt, buf ^ 1);   // that buffer's last readers finished before the __syncwarp below
+        mbar_wait(smem_u32(&s_bar[warp][buf]), phase[buf]);
+        phase[buf] ^= 1;
         __syncwarp();
+        const uint32_t *src_t = s_src[warp][buf];
+        const uint32_t *dst_t = s_dst[warp][buf];
+        const uint32_t p = cur.p;
+        const int n = cur.n, M = cur.M, Mp = cur.Mp, r0 = cur.r0, ub = cur.ub;
 
         const int n_steps = min(MATCH_R / 32, (n - r0 + 31) / 32);
         for (int step = 0; step < n_steps; step++) {
@@ -547,7 +595,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                                 uint32_t mine = 0;
 #pragma unroll
                                 for (int c = 0; c < MATCH_C; c++) mine |= (mx[c] <= T ? 1u : 0u) << c;
-                                coop_verify(ectx, p, src_t, dst_t, step, r0 + 32 * step, ub, M, n, lanes_alive, mine, lane);
+                                coop_verify(ectx, p, src_t, dst_t, step, r0 + 32 * step, ub, Mp, M, n, lanes_alive, mine, lane);
                                 alive = false;   // this word is done
                             }
                         }
@@ -599,10 +647,13 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                 while (f) {
                     const int c = __ffs((int)f) - 1;
                     f &= f - 1;
-                    full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, M, n, lane);
+                    full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, Mp, M, n, lane);
                 }
             }
         }
+        __syncwarp();   // every lane is done with this buffer: the tile after next may land in it
+        cur = nxt;
+        have = have_next;
     }
 }
 
@@ -712,6 +763,21 @@ __global__ void seg_lmin_kernel(const uint64_t *__restrict__ ts, const SegTab *_
     atomicMin(&lmin[seg], len < 1u ? 1u : len);
 }
 
+// The fast kernel's view of a list as a dst: its live columns 1 .. len-1, padded to a period that is a
+// multiple of 4 and repeated often enough that any 512-column window of the wrapped list is one span.
+struct Dst2Seg {
+    uint32_t dev_offset, len, out_off, period, reps;
+};
+__global__ void dst2_build_kernel(const uint32_t *__restrict__ hashes, const Dst2Seg *__restrict__ segs,
+                                  uint32_t *__restrict__ out) {
+    const Dst2Seg sg = segs[blockIdx.y];
+    const uint32_t total = sg.period * sg.reps;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+        const uint32_t c = x % sg.period;
+        out[sg.out_off + x] = c + 1 < sg.len ? hashes[sg.dev_offset + 1 + c] : 0u;
+    }
+}
+
 // ------------------------------------------------------------------- host
 
 // Enqueue the whole match stage on ctx->stream without waiting for anything:
@@ -722,7 +788,11 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
                   const nb200_match_params *params, uint32_t pair_base, uint32_t run_cap_min, MatchPending *out,
                   DeviceRun *ext_runs, uint32_t ext_cap) {
     nb200_hashset *hs = const_cast<nb200_hashset *>(hs_c);
-    if (params->hash_match_threshold > 32) return NB200_ERR_INVALID_ARGUMENT;
+    // the reference takes any u16 threshold (comparator.rs:76); above 32 every cell with i, j >= 1
+    // matches, exactly as with 32, so the kernels see min(T, 32) (the vote's bias T + T/2 keeps T)
+    nb200_match_params clamped = *params;
+    clamped.hash_match_threshold = std::min<uint32_t>(params->hash_match_threshold, 32u);
+    params = &clamped;
     NB_CUDA(cudaSetDevice(ctx->device));
     std::vector<uint32_t> default_flat;
     if (!pairs) {
@@ -738,6 +808,20 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     out->problem_is_ending.clear();
 
     PhaseTimer phase_setup(ctx, NB200_PHASE_MATCH_SETUP);
+    // every list as a dst of the fast kernel: period and place of its repeated live columns
+    const uint32_t nseg_all = 2 * hs->n_videos;
+    std::vector<Dst2Seg> d2(nseg_all);
+    uint64_t d2_total = 0;
+    uint32_t d2_max = 1;
+    for (uint32_t k = 0; k < nseg_all; k++) {
+        const uint32_t len = hs->seg_len[k];
+        const uint32_t period = len >= 2 ? ((len - 1 + 3) & ~3u) : 4u;
+        const uint32_t reps = std::max<uint32_t>(2u, (FAST_DST_TILE + period - 1) / period + 1);
+        d2[k] = {hs->dev_offset[k], len, (uint32_t)d2_total, period, reps};
+        d2_total += (uint64_t)period * reps;
+        d2_max = std::max(d2_max, period * reps);
+        if (d2_total > 0xfffffff0ull) return NB200_ERR_TOO_LARGE;
+    }
     // problems, tiled for the fast kernel (wrapped diagonals) and for the general one
     std::vector<MatchProblem> prob_f, prob_g;
     prob_f.reserve(n_pairs * (endings ? 2 : 1));
@@ -762,8 +846,10 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
             pr.group = (uint32_t)(2 * (k + pair_base) + (uint64_t)e);
             pr.src_seg = sa;
             pr.dst_seg = sb;
+            pr.dst2_off = d2[sb].out_off;
+            pr.period = d2[sb].period;
             const uint64_t chunks = (n + MATCH_R - 1) / MATCH_R;
-            pr.n_bands = (uint32_t)(((uint64_t)m - 1 + MATCH_DW - 1) / MATCH_DW);
+            pr.n_bands = (uint32_t)(((uint64_t)pr.period + MATCH_DW - 1) / MATCH_DW);
             pr.tile_begin = (uint32_t)tiles_f;
             tiles_f += chunks * pr.n_bands;
             prob_f.push_back(pr);
@@ -826,6 +912,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         return off;
     };
     const size_t o_tab = carve((size_t)nseg * sizeof(SegTab)), o_lmin = carve((size_t)nseg * sizeof(uint32_t));
+    const size_t o_d2 = carve((size_t)nseg * sizeof(Dst2Seg));
     const size_t b_prob = (size_t)n_problems * sizeof(MatchProblem), b_tend = (size_t)n_problems * sizeof(uint32_t);
     const size_t o_prob_f = carve(b_prob), o_tend_f = carve(b_tend), o_lut_f = carve(lut_f.size() * sizeof(uint32_t));
     const size_t o_prob_g = carve(b_prob), o_tend_g = carve(b_tend), o_lut_g = carve(lut_g.size() * sizeof(uint32_t));
@@ -833,7 +920,9 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     // stage enqueued on this context must be through with them.  Normally it is (every search
     // ends with a synchronisation); two nb200_match_export calls back to back are the exception.
     NB_CUDA(cudaEventSynchronize(ctx->ev_chunk[10]));
-    if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_problems.reserve(total) != NB200_OK) return NB200_ERR_CUDA;
+    if (ctx->h_stage.reserve(total) != NB200_OK || ctx->d_problems.reserve(total) != NB200_OK ||
+        (want_fast && ctx->d_dst2.reserve((size_t)(d2_total + 16) * sizeof(uint32_t)) != NB200_OK))
+        return NB200_ERR_CUDA;
     char *st = ctx->h_stage.as<char>();
     char *arena = ctx->d_problems.as<char>();
     SegTab *const d_segtab = reinterpret_cast<SegTab *>(arena + o_tab);
@@ -854,6 +943,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
             max_len = std::max(max_len, hs->seg_len[k]);
         }
     }
+    memcpy(st + o_d2, d2.data(), (size_t)nseg * sizeof(Dst2Seg));
     if (want_fast) {
         memcpy(st + o_prob_f, prob_f.data(), b_prob);
         memcpy(st + o_tend_f, tend_f.data(), b_tend);
@@ -885,6 +975,15 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     auto grid_for = [&](uint64_t n_tiles) {
         return std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
     };
+    if (want_fast) {
+        // the repeated dst lists (a few MB at most): rebuilt with every match, the season may be a
+        // view over buffers that K2 or an all-gather has just rewritten
+        dst2_build_kernel<<<dim3(std::min<uint32_t>((d2_max + 255) / 256, 64u), nseg), 256, 0, s>>>(
+            hs->d_hashes.as<uint32_t>(), reinterpret_cast<const Dst2Seg *>(arena + o_d2), ctx->d_dst2.as<uint32_t>());
+        NB_CUDA(cudaGetLastError());
+        ctx->n_launches++;
+    }
+    args.dst2 = ctx->d_dst2.as<uint32_t>();
     NB_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (want_fast) {
         args.problems = d_prob_f;

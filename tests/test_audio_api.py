@@ -56,6 +56,20 @@ def test_header_md5_and_discovery(tmp_path):
         audio.find_video_files([str(tmp_path / "nope")])
 
 
+def test_skip_file_bytes_are_what_serde_json_writes(tmp_path):
+    """f32 seconds in their shortest round-tripping form, as serde_json (ryu) prints them
+    (comparator.rs:329-354): 12.3, not 12.300000190734863."""
+    v = tmp_path / "ep.wav"
+    v.write_bytes(b"\0" * 9000)
+    audio.Comparator.create_skip_file(str(v), audio.SearchResult(opening=(12_300_000_000, 99_000_000_000)))
+    text = (tmp_path / "ep.needle.skip.json").read_text()
+    assert text.startswith('{"opening":[12.3,99.0],"ending":null,"md5":"')
+    for x, want in ((12.3, "12.3"), (12.0, "12.0"), (0.0, "0.0"), (1e-5, "1e-5"), (3.5e-7, "3.5e-7"), (1e16, "1e16"),
+                    (2.6, "2.6"), (1234.5678, "1234.5677")):
+        assert audio.json_f32(x) == want
+        assert np.float32(float(audio.json_f32(x))) == np.float32(x)
+
+
 def test_skip_file_roundtrip(tmp_path):
     v = tmp_path / "ep.wav"
     write_wav(v, np.zeros(10_000, np.int16))

@@ -159,6 +159,9 @@ def test_threshold_extremes(ctx, oracle):
     check_season(ctx, oracle, season, threshold=32, include_endings=True)   # every cell matches
     check_season(ctx, oracle, season, threshold=32, include_endings=True, min_opening_ns=0, min_ending_ns=0)
     check_season(ctx, oracle, season, threshold=0, include_endings=True, min_opening_ns=0, min_ending_ns=0)
+    # the reference takes any u16 threshold (comparator.rs:76): above 32 the match is what 32 gives, the
+    # vote's clustering bias T + T/2 keeps the caller's T
+    check_season(ctx, oracle, season, threshold=40, include_endings=True)
 
 
 def test_identical_videos_threshold_zero(ctx, oracle):
