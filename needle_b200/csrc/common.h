@@ -153,6 +153,20 @@ struct PinnedBuf {
 
 // ---------------------------------------------------------------- objects
 
+namespace nb200 {
+// What the host derived for the last match stage on a context and left in its device arena
+// (match.cu: match_enqueue); reused when the next stage has the same lists, pairs and parameters.
+struct MatchPlanCache {
+    bool valid = false;
+    uint64_t key = 0;
+    uint32_t n_problems = 0, d2_max = 1, max_len = 1;
+    uint64_t tiles_f = 0, tiles_g = 0, cells = 0, d2_total = 0;
+    size_t o_tab = 0, o_lmin = 0, o_d2 = 0, o_prob_f = 0, o_tend_f = 0, o_lut_f = 0, o_prob_g = 0, o_tend_g = 0, o_lut_g = 0;
+    std::vector<uint32_t> problem_pair;
+    std::vector<uint8_t> problem_is_ending;
+};
+}  // namespace nb200
+
 struct nb200_ctx {
     int device = 0;
     int sm_count = 148;
@@ -174,6 +188,7 @@ struct nb200_ctx {
     bool defer_wait = false;            // *_into fingerprint calls return without waiting for the stream
     bool host_vote = false;             // searches download the runs and vote on the host (vote.cpp) instead of on the device
     nb200::DevBuf d_problems;   // the match stage's descriptor arena: segment table, run-length bounds, both tilings
+    nb200::MatchPlanCache match_plan;   // what that arena currently holds
     nb200::DevBuf d_counters, d_runs, d_dst2;   // d_dst2: the fast match kernel's repeated dst lists
     nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
     nb200::PinnedBuf h_fp_stage, h_vote_stage, h_results;   // one staging area per phase: nothing waits for a copy to drain

@@ -140,7 +140,9 @@ def test_analyze_then_search_flow(ctx, oracle, tmp_path, capsys):
         assert abs(r.opening[0] / 1e9 - ep.intro_at) < 4.0
         assert abs(r.ending[0] / 1e9 - ep.credits_at) < 4.0
         skip = json.loads(open(audio._with_extension(v, "needle.skip.json")).read())
-        assert skip["opening"] == [audio.duration_as_secs_f32(r.opening[0]), audio.duration_as_secs_f32(r.opening[1])]
+        # the file holds the shortest decimal of each f32 (serde_json): equal as f32, not as text of the double
+        assert [np.float32(x) for x in skip["opening"]] == [np.float32(audio.duration_as_secs_f32(r.opening[0])),
+                                                            np.float32(audio.duration_as_secs_f32(r.opening[1]))]
     # bit-exact against the oracle on the GPU's own hashes
     season = H.season_from_lists([f.opening_data() for f in frame_hashes], [f.ending_data() for f in frame_hashes])
     st, want, _ = H.oracle_run(oracle, season, **H.params_kw(include_endings=True))
