@@ -888,7 +888,9 @@ int nb200_mjob_run(nb200_mjob *j, const int16_t *const *host_pcm, nb200_search_r
             nb200_ctx *ctx = R.comm->ctx;
             NB_CUDA(cudaSetDevice(ctx->device));
             NB_CUDA(cudaEventRecord(R.ev[0], ctx->stream));
-            if (host_pcm) {
+            if (R.my_segments.empty()) {
+                // more ranks than videos: this one only matches
+            } else if (host_pcm) {
                 std::vector<const int16_t *> p;
                 for (uint32_t s : R.my_segments) {
                     if (!host_pcm[s] && j->n_mono[s]) return NB200_ERR_NULL_ARGUMENT;
