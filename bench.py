@@ -240,8 +240,8 @@ def run_b200(args):
     # a stuck collective must not hold the GPU box until the driver's limit: dump every thread's stack and leave
     import faulthandler
     faulthandler.dump_traceback_later(float(os.environ.get("NB200_BENCH_WATCHDOG_S", "600")), exit=True)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"    # NCCL's version banner goes to stdout; this run prints one JSON line
+    # NCCL's banner and warnings go to stderr: stdout carries one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     from needle_b200 import engine
 
