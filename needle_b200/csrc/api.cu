@@ -4,6 +4,7 @@
 // (needle/src/audio/comparator.rs:532-578).  The kernels live in match.cu and
 // fingerprint.cu, the host vote in vote.cpp, .needle.dat I/O in persist.cpp.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -15,6 +16,10 @@
 namespace nb200 {
 
 static thread_local std::string g_last_error;
+uint64_t next_object_uid() {
+    static std::atomic<uint64_t> counter{1};
+    return counter.fetch_add(1);
+}
 
 void set_last_error(const char *what, cudaError_t e) {
     g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
@@ -204,7 +209,7 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
         return NB200_OK;
     case NB200_OPT_K1_VARIANT:
         if (value != 0 && value != 1 && value != 8 && value != 10 && value != 12 && value != 16 && value != 17 &&
-            value != 112)
+            value != 18 && value != 112)
             return NB200_ERR_INVALID_ARGUMENT;
         ctx->k1_variant = (int)value;
         return NB200_OK;
@@ -512,6 +517,7 @@ int nb200_hashset_view(nb200_ctx *ctx, const void *d_hashes, const void *d_ts_ns
     hs->d_hashes.borrow(const_cast<void *>(d_hashes), extent * sizeof(uint32_t));
     hs->d_ts.borrow(const_cast<void *>(d_ts_ns), extent * sizeof(uint64_t));
     hs->sorted_layout = false;
+    hs->immutable = false;
     *out = hs;
     return NB200_OK;
 }

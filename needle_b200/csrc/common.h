@@ -154,11 +154,13 @@ struct PinnedBuf {
 // ---------------------------------------------------------------- objects
 
 namespace nb200 {
+uint64_t next_object_uid();
 // What the host derived for the last match stage on a context and left in its device arena
 // (match.cu: match_enqueue); reused when the next stage has the same lists, pairs and parameters.
 struct MatchPlanCache {
     bool valid = false;
     uint64_t key = 0;
+    uint64_t data_uid = 0;   // immutable hashset whose bounds and repeated lists the arena / d_dst2 hold (0: none)
     uint32_t n_problems = 0, d2_max = 1, max_len = 1;
     uint64_t tiles_f = 0, tiles_g = 0, cells = 0, d2_total = 0;
     size_t o_tab = 0, o_lmin = 0, o_d2 = 0, o_prob_f = 0, o_tend_f = 0, o_lut_f = 0, o_prob_g = 0, o_tend_g = 0, o_lut_g = 0;
@@ -201,7 +203,7 @@ struct nb200_ctx {
     nb200::DevBuf d_tsfill;
     // fingerprint stage: constant tables (built once per context) and scratch
     bool fp_ready = false;
-    nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes, d_fp_wsplit;
+    nb200::DevBuf d_fp_window, d_fp_twiddle, d_fp_lane, d_fp_notes, d_fp_wsplit, d_fp_window_odd;
     int k1_variant = 0;   // NB200_OPT_K1_VARIANT (include/needle_b200.h)
     nb200::DevBuf d_chroma, d_fp_desc, d_stereo;
 };
@@ -217,6 +219,11 @@ struct nb200_hashset {
     uint64_t dev_total = 0;             // aligned element count
     nb200::DevBuf d_hashes, d_ts;
     bool sorted_layout = true;          // dev_offset ascending with the segment index (false for views)
+    // Identity of the DATA, for what the match stage derives from it on the device (run-length bounds,
+    // repeated dst lists): a set the library filled itself never changes after creation; a view is
+    // over buffers the caller (K2, an all-gather) may rewrite between two searches.
+    uint64_t uid = nb200::next_object_uid();
+    bool immutable = true;
 };
 
 struct nb200_pcmset {
@@ -303,7 +310,8 @@ int vote_enqueue(nb200_ctx *ctx, const DeviceRun *d_runs, const unsigned int *d_
 int vote_blocks_impl(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes, uint64_t cap,
                      const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                      uint64_t n_pairs, const nb200_match_params *params, int do_vote,
-                     nb200_search_result *results, uint64_t *max_found);
+                     nb200_search_result *results, uint64_t *max_found, int (*blocks_consumed)(void *) = nullptr,
+                     void *consumed_arg = nullptr);
 
 // vote.cpp ---------------------------------------------------------------
 void default_pairs(uint32_t n_videos, std::vector<uint32_t> &flat);   // (i<j) reference order

@@ -202,6 +202,7 @@ struct K1Args {
     const float2 *twiddle;   // [32][64] W_2048^(n2 k1)
     const float2 *lane_w;    // [32] W_4096^L
     const float2 *wsplit;    // [41][32] W_4096^(L + 32 t)
+    const float2 *window_odd;   // [1056] (w[2n-1], w[2n]) / 32767, entry 0 = (w[4095], w[0]): frames rotated by one sample
     float *chroma;           // [total_frames][12]
 };
 
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_h32_kernel(const K1A
 constexpr int TM_ROWS = 32;
 constexpr int TM_WARP_BYTES = TM_ROWS * XCHG_STRIDE * 8;     // 8,448 B
 static_assert(PCM_COPY_BYTES <= TM_WARP_BYTES, "PCM must fit the exchange buffer");
-template <int NW> constexpr int tm_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * TM_WARP_BYTES + NW * 8 + 16 + FP_T * 32 * 8; }
+template <int NW> constexpr int tm_smem_bytes() { return (FP_HALF / 2 + FP_HALF) * 8 + NW * TM_WARP_BYTES + NW * 8 + 16 + FP_T * 32 * 8 + 1056 * 8; }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -773,6 +774,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_warp + NW * TM_WARP_BYTES);
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + NW);
     f2 *s_wsplit = reinterpret_cast<f2 *>(s_tmem + 4);                   // REV >= 2: [41][32] W_4096^(L + 32 t)
+    f2 *s_window_odd = s_wsplit + FP_T * 32;                             // REV >= 3: 1056 pairs (w[2n-1], w[2n]), see below
 
     const int lane = threadIdx.x & 31;
     // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps what
@@ -782,6 +784,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
         if (i < FP_HALF / 2) s_window[i] = a.window[i];
         s_twiddle[i] = a.twiddle[i];
         if (REV >= 2 && i < FP_T * 32) s_wsplit[i] = a.wsplit[i];
+        if (REV >= 3 && i < 1056) s_window_odd[i] = a.window_odd[i];
     }
     if (threadIdx.x < NW) mbar_init(smem_u32(s_bar + threadIdx.x), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -819,12 +822,29 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
     uint32_t frame = a.frame_begin + blk * NW + warp;
     uint32_t phase = 0;
     uint32_t delta = 0;
+    // REV >= 3: a frame whose first sample sits at an odd 2-byte position (every other frame: the hop is
+    // 1365 samples) is fetched from ONE SAMPLE EARLIER, which makes its sample pairs 4-byte aligned words,
+    // and transformed as the frame rotated by one sample: v = (xw[4095], xw[0], .., xw[4094]).  A circular
+    // shift multiplies the spectrum by a unit-modulus phase: the power spectrum -- all that Chromaprint
+    // takes from the FFT -- is the same.  The window for those frames is the window shifted by one
+    // (s_window_odd), and the one sample that wraps around (xw[4095] in place of the sample before the
+    // frame) is patched into lane 0's first value.  Every frame then costs one LDS per complex value
+    // and no funnel shift.  `odd` travels in bit 4 of delta.
+    auto frame_bytes = [&](uint32_t f) -> const unsigned char * {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(frame_src(a, f));
+        uint32_t odd = 0;
+        if (REV >= 3) {
+            odd = (uint32_t)(reinterpret_cast<uintptr_t>(src) >> 1) & 1u;
+            src -= 2 * odd;
+        }
+        delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15) | (odd << 4);
+        return src - (delta & 15);
+    };
     if (blk < n_blocks && frame < a.frame_end) {
-        const int16_t *src = frame_src(a, frame);
-        delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+        const unsigned char *base = frame_bytes(frame);
         if (lane == 0) {
             mbar_expect_tx(bar, PCM_COPY_BYTES);
-            bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+            bulk_g2s(xchg_addr, base, PCM_COPY_BYTES, bar);
         }
     }
 
@@ -835,14 +855,19 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
         f2 v[32];
         mbar_wait(bar, phase);
         phase ^= 1;
-        const uint32_t *p = pcm_words + (delta >> 2) + lane;
+        const uint32_t *p = pcm_words + ((delta & 15) >> 2) + lane;
         const uint32_t shift = (delta & 2) * 8;
+        const bool odd = REV >= 3 && (delta & 16) != 0;
+        // rotated frame: the sample that wraps around, x[4095], is the low half of word 2048
+        float wrap = 0.f;
+        if (REV >= 3) wrap = (float)(short)(pcm_words[((delta & 15) >> 2) + 2048] & 0xffffu);
         // ---- pass 1: even rows (half = 0), then odd rows (half = 1); one copy of the code
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             const uint32_t *ph = p + 32 * half;
-            const f2 *wlo = s_window + 32 * half + lane;
-            const f2 *whi = s_window + 32 * (63 - half) + 31 - lane;
+            const f2 *wt = odd ? s_window_odd : s_window;
+            const f2 *wlo = wt + 32 * half + lane;
+            const f2 *whi = wt + 32 * (63 - half) + (odd ? 32 : 31) - lane;
             if (REV >= 2) {
                 // window and first radix-2 layer of the 32-point FFT in one: c = s w, (c0 + s2 w2, 2 c0 - that);
                 // the samples go through the conversion unit (I2F.S16 on each half of the word)
@@ -852,9 +877,17 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int j = n1 + 8 * i;
-                        const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
-                        sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
+                        if (REV >= 3) {
+                            sv[i] = s16x2_to_float_xu(ph[64 * j]);
+                        } else {
+                            const uint32_t w0 = ph[64 * j], w1 = ph[64 * j + 1];
+                            sv[i] = s16x2_to_float_xu(__funnelshift_r(w0, w1, shift));
+                        }
                         wv[i] = j < 16 ? wlo[64 * j] : swp(whi[-64 * j]);
+                    }
+                    if (REV >= 3 && n1 == 0) {
+                        // value 0 of the rotated frame (lane 0, row 0, first half): (x[4095], x[0])
+                        if (odd && half == 0 && lane == 0) sv[0].x = wrap;
                     }
                     const f2 c0 = mul2(sv[0], wv[0]), c1 = mul2(sv[1], wv[1]);
                     const f2 d0 = fma2(sv[2], wv[2], c0), d2 = fma2(sv[3], wv[3], c1);
@@ -949,12 +982,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                 const uint32_t nblk = blk + gridDim.x;
                 const uint32_t nframe = a.frame_begin + nblk * NW + warp;
                 if (nblk < n_blocks && nframe < a.frame_end) {
-                    const int16_t *src = frame_src(a, nframe);
-                    delta = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+                    const unsigned char *base = frame_bytes(nframe);
                     fence_proxy_async();
                     if (lane == 0) {
                         mbar_expect_tx(bar, PCM_COPY_BYTES);
-                        bulk_g2s(xchg_addr, reinterpret_cast<const unsigned char *>(src) - delta, PCM_COPY_BYTES, bar);
+                        bulk_g2s(xchg_addr, base, PCM_COPY_BYTES, bar);
                     }
                 }
             }
@@ -1232,6 +1264,14 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
         const double ang = -2.0 * PI * l / FP_FRAME;
         lane_w[l] = make_float2((float)cos(ang), (float)sin(ang));
     }
+    // the window shifted by one sample, for frames that are transformed rotated by one (K1, REV >= 3):
+    // pair n = (w[2n-1], w[2n]); pair 0 = (w[4095], w[0]); pairs above 1024 are the swapped mirror images
+    std::vector<float2> window_odd(1056, make_float2(0.f, 0.f));
+    {
+        auto wnd = [&](int i) { return (1.0 / 32767.0) * (0.54 - 0.46 * cos(i * 2.0 * PI / (FP_FRAME - 1))); };
+        for (int n = 0; n <= 1024; n++)
+            window_odd[n] = make_float2((float)wnd(n == 0 ? FP_FRAME - 1 : 2 * n - 1), (float)wnd(2 * n));
+    }
     std::vector<float2> wsplit(FP_T * 32);
     for (int k = 0; k < FP_T * 32; k++) {
         const double ang = -2.0 * PI * k / FP_FRAME;
@@ -1272,6 +1312,8 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaMemcpy(ctx->d_fp_window.p, window.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_twiddle.p, tw.data(), sizeof(float2) * FP_HALF, cudaMemcpyHostToDevice));
     NB_CUDA(cudaMemcpy(ctx->d_fp_lane.p, lane_w.data(), sizeof(float2) * 32, cudaMemcpyHostToDevice));
+    NB_TRY(ctx->d_fp_window_odd.alloc(sizeof(float2) * window_odd.size()));
+    NB_CUDA(cudaMemcpy(ctx->d_fp_window_odd.p, window_odd.data(), sizeof(float2) * window_odd.size(), cudaMemcpyHostToDevice));
     NB_TRY(ctx->d_fp_wsplit.alloc(sizeof(float2) * wsplit.size()));
     NB_CUDA(cudaMemcpy(ctx->d_fp_wsplit.p, wsplit.data(), sizeof(float2) * wsplit.size(), cudaMemcpyHostToDevice));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1285,6 +1327,8 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<16>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<12>()));
@@ -1392,19 +1436,22 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         k1.twiddle = ctx->d_fp_twiddle.as<float2>();
         k1.lane_w = ctx->d_fp_lane.as<float2>();
         k1.wsplit = ctx->d_fp_wsplit.as<float2>();
+        k1.window_odd = ctx->d_fp_window_odd.as<float2>();
         k1.chroma = ctx->d_chroma.as<float>();
         // K1 over global frames [f0, f1)
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
             const uint32_t nf = f1 - f0;
-            const int variant = ctx->k1_variant == 0 ? 17 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM, revision-2 arithmetic
+            const int variant = ctx->k1_variant == 0 ? 18 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM, revision-2 arithmetic
             if (variant >= 16) {
                 // tensor-memory kernel: 16 (or, variant 112, 12) warps per SM
                 k1.frame_begin = f0;
                 k1.frame_end = f1;
                 const uint32_t nw = variant == 112 ? 12u : 16u;
                 const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
-                if (variant == 17)
+                if (variant == 18)
+                    fp_fft_chroma_tm_kernel<16, 3><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                else if (variant == 17)
                     fp_fft_chroma_tm_kernel<16, 2><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
                 else if (nw == 16)
                     fp_fft_chroma_tm_kernel<16, 1><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);

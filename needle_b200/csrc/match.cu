@@ -995,7 +995,10 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     DeviceRun *const runs_out = ext_runs ? ext_runs : ctx->d_runs.as<DeviceRun>();
     out->run_cap = run_cap;
     if (ctx->d_counters.reserve(64) != NB200_OK) return NB200_ERR_CUDA;
-    NB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, s));
+    // the same immutable season as last time: its run-length bounds, the problems' lcand, the smallest
+    // lcand (counters[3]) and the repeated dst lists are still on the device
+    const bool same_data = hit && hs->immutable && pc.data_uid == hs->uid;
+    NB_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, same_data ? 12 : 64, s));
     ctx->ev_valid[2] = ctx->ev_valid[3] = false;
     if (n_problems == 0) return NB200_OK;
     if (want_fast && ctx->d_dst2.reserve((size_t)(d2_total + 16) * sizeof(uint32_t)) != NB200_OK) return NB200_ERR_CUDA;
@@ -1006,14 +1009,16 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     MatchProblem *const d_prob_g = reinterpret_cast<MatchProblem *>(arena + pc.o_prob_g);
     const size_t o_d2 = pc.o_d2, o_tend_f = pc.o_tend_f, o_lut_f = pc.o_lut_f, o_tend_g = pc.o_tend_g, o_lut_g = pc.o_lut_g;
 
-    seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
-        hs->d_ts.as<uint64_t>(), d_segtab, params->min_opening_ns, params->min_ending_ns, d_lmin);
-    NB_CUDA(cudaGetLastError());
-    ctx->n_launches++;
-    problem_finalize_kernel<<<(n_problems + 255) / 256, 256, 0, s>>>(want_fast ? d_prob_f : nullptr, d_prob_g, d_lmin,
-                                                                      n_problems, ctx->d_counters.as<unsigned int>());
-    NB_CUDA(cudaGetLastError());
-    ctx->n_launches++;
+    if (!same_data) {
+        seg_lmin_kernel<<<dim3((max_len + 255) / 256, nseg), 256, 0, s>>>(
+            hs->d_ts.as<uint64_t>(), d_segtab, params->min_opening_ns, params->min_ending_ns, d_lmin);
+        NB_CUDA(cudaGetLastError());
+        ctx->n_launches++;
+        problem_finalize_kernel<<<(n_problems + 255) / 256, 256, 0, s>>>(want_fast ? d_prob_f : nullptr, d_prob_g, d_lmin,
+                                                                          n_problems, ctx->d_counters.as<unsigned int>());
+        NB_CUDA(cudaGetLastError());
+        ctx->n_launches++;
+    }
 
     MatchArgs args;
     args.hashes = hs->d_hashes.as<uint32_t>();
@@ -1025,14 +1030,15 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     auto grid_for = [&](uint64_t n_tiles) {
         return std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
     };
-    if (want_fast) {
-        // the repeated dst lists (a few MB at most): rebuilt with every match, the season may be a
-        // view over buffers that K2 or an all-gather has just rewritten
+    if (want_fast && !same_data) {
+        // the repeated dst lists (a few MB at most): rebuilt with every match unless the season is the
+        // same immutable one -- a view may be over buffers that K2 or an all-gather has just rewritten
         dst2_build_kernel<<<dim3(std::min<uint32_t>((d2_max + 255) / 256, 64u), nseg), 256, 0, s>>>(
             hs->d_hashes.as<uint32_t>(), reinterpret_cast<const Dst2Seg *>(arena + o_d2), ctx->d_dst2.as<uint32_t>());
         NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
     }
+    pc.data_uid = hs->immutable ? hs->uid : 0;
     args.dst2 = ctx->d_dst2.as<uint32_t>();
     NB_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (want_fast) {

@@ -17,10 +17,11 @@
 //       of the block is stored directly into rank 0's HBM (peer pointer; CUDA IPC
 //       between processes), then a system-scope release flag; rank 0's vote waits on
 //       the flags of all ranks.  No fixed-size collective, no host round trip.
-//   rank 0: heap replay + find_best_match on the device, 48 bytes per video to the
-//       host; an acknowledgement word (step, largest run count) is stored into every
-//       peer's memory, which is what the peers' call returns on (and how every rank
-//       learns that a block overflowed and the step must be repeated with more room).
+//   rank 0: as soon as all blocks have landed an acknowledgement word (step, largest run
+//       count) is stored into every peer's memory -- what the peers' call returns on, and
+//       how every rank learns that a block overflowed and the step must be repeated with
+//       more room -- then heap replay + find_best_match on the device, 48 bytes per video
+//       to the host.
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -135,14 +136,22 @@ __global__ void wait_flags_kernel(uint32_t *ctrl, uint32_t world, uint32_t step)
     }
 }
 
-// rank 0, after its vote: (info, step) into every rank's control block (its own included)
+// rank 0, as soon as every block has landed: the largest run count of the step and the step number
+// into every rank's control block (its own included) -- the peers return on it while rank 0 votes
 struct AckTargets {
     uint32_t *ctrl[64];
 };
-__global__ void ack_kernel(const AckTargets t, uint32_t world, uint32_t step, uint32_t info) {
+__global__ void __launch_bounds__(64) ack_kernel(const char *__restrict__ recv, uint64_t block_stride, const AckTargets t,
+                                                 uint32_t world, uint32_t step) {
+    __shared__ uint32_t s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    if (threadIdx.x < world)
+        atomicMax(&s_max, reinterpret_cast<const RunBlockHeader *>(recv + (size_t)threadIdx.x * block_stride)->n_found);
+    __syncthreads();
     if (threadIdx.x < world) {
         uint32_t *c = t.ctrl[threadIdx.x];
-        c[CTRL_ACK_INFO] = info;
+        c[CTRL_ACK_INFO] = min(s_max, 0xfffffff0u);
         __threadfence_system();
         st_release_sys(c + CTRL_ACK_STEP, step);
     }
@@ -639,26 +648,29 @@ static int mjob_tail(nb200_mjob *j, nb200_search_result *results) {
                 wait_flags_kernel<<<1, 64, 0, ctx->stream>>>(c->d_ctrl, (uint32_t)world, c->step);
                 NB_CUDA(cudaGetLastError());
                 ctx->n_launches++;
+                NB_CUDA(cudaMemcpyAsync(c->h_ack.as<uint32_t>() + 4, c->d_ctrl + CTRL_TIMEOUT, 4, cudaMemcpyDeviceToHost, ctx->stream));
                 blocks = c->d_recv;
                 stride_bytes = c->recv_block_bytes;
             }
             NB_CUDA(cudaEventRecord(R.ev[4], ctx->stream));
+            // the acknowledgement goes out once the blocks have been compacted out of the receive area
+            // (the peers may push their next step into it from then on), while the vote is still running
+            auto release_peers = [](void *arg) -> int {
+                nb200_comm *c0 = static_cast<nb200_comm *>(arg);
+                ack_kernel<<<1, 64, 0, c0->ctx->stream>>>(c0->d_recv, c0->recv_block_bytes, c0->ack_targets,
+                                                          (uint32_t)c0->world, c0->step);
+                NB_CUDA(cudaGetLastError());
+                c0->ctx->n_launches++;
+                return NB200_OK;
+            };
             st0 = vote_blocks_impl(ctx, blocks, (uint32_t)world, stride_bytes, j->run_cap, j->hash_durations.data(),
                                    j->n_videos, j->default_pairs ? nullptr : pairs,
-                                   j->default_pairs ? 0 : j->pairs.size() / 2, &j->params, 1, results, &max_found);
+                                   j->default_pairs ? 0 : j->pairs.size() / 2, &j->params, 1, results, &max_found,
+                                   world > 1 ? +release_peers : nullptr, c);
             NB_CUDA(cudaEventRecord(R.ev[5], ctx->stream));
-            if (world > 1) {
-                // TOO_LARGE travels as the run count; any other failure as 0xffffffff
-                const uint32_t info = (st0 == NB200_OK || st0 == NB200_ERR_TOO_LARGE)
-                                          ? (uint32_t)std::min<uint64_t>(max_found, 0xfffffff0ull) : 0xffffffffu;
-                ack_kernel<<<1, 64, 0, ctx->stream>>>(c->ack_targets, (uint32_t)world, c->step, info);
-                NB_CUDA(cudaGetLastError());
-                ctx->n_launches++;
-            }
             NB_CUDA(cudaStreamSynchronize(ctx->stream));
             if (world > 1) {
-                uint32_t timed_out = 0;
-                NB_CUDA(cudaMemcpy(&timed_out, c->d_ctrl + CTRL_TIMEOUT, 4, cudaMemcpyDeviceToHost));
+                const uint32_t timed_out = c->h_ack.as<uint32_t>()[4];
                 if (timed_out) {
                     NB_CUDA(cudaMemset(c->d_ctrl + CTRL_TIMEOUT, 0, 4));
                     set_last_error_msg("rank " + std::to_string(timed_out - 1) + " did not deliver its run block in time");
@@ -679,8 +691,8 @@ static int mjob_tail(nb200_mjob *j, nb200_search_result *results) {
             ctx->n_launches++;
             NB_CUDA(cudaMemcpyAsync(h, c->d_ctrl + 96, 8, cudaMemcpyDeviceToHost, ctx->stream));
             NB_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (h[0] >= 0xfffffffeu) {   // rank 0 failed (its caller has the reason) or never answered
-                set_last_error_msg(h[0] == 0xfffffffeu ? "rank 0 did not acknowledge the step in time" : "rank 0 failed the step");
+            if (h[0] == 0xfffffffeu) {
+                set_last_error_msg("rank 0 did not acknowledge the step in time");
                 st_peer = NB200_ERR_STATE;
             }
             else if (!have0) max_found = std::max<uint64_t>(max_found, h[0]);

@@ -420,7 +420,7 @@ int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, u
                       nb200_search_result *results, uint64_t *max_found) {
     if (block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0) return NB200_ERR_INVALID_ARGUMENT;
     return vote_blocks_impl(ctx, d_blocks, n_blocks, block_bytes, (block_bytes - sizeof(RunBlockHeader)) / sizeof(DeviceRun),
-                            hash_duration_ns, n_videos, pairs, n_pairs, params, do_vote, results, max_found);
+                            hash_duration_ns, n_videos, pairs, n_pairs, params, do_vote, results, max_found, nullptr, nullptr);
 }
 
 }  // extern "C"
@@ -430,7 +430,8 @@ int nb200_vote_blocks(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, u
 int nb200::vote_blocks_impl(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blocks, uint64_t block_bytes, uint64_t cap,
                             const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_t (*pairs)[2],
                             uint64_t n_pairs, const nb200_match_params *params, int do_vote,
-                            nb200_search_result *results, uint64_t *max_found) {
+                            nb200_search_result *results, uint64_t *max_found, int (*blocks_consumed)(void *),
+                            void *consumed_arg) {
     if (!ctx || !d_blocks || !hash_duration_ns || !params || !max_found) return NB200_ERR_NULL_ARGUMENT;
     if (do_vote && !results) return NB200_ERR_NULL_ARGUMENT;
     if (n_blocks == 0 || block_bytes < 2 * sizeof(RunBlockHeader) || block_bytes % 64 != 0 ||
@@ -454,6 +455,8 @@ int nb200::vote_blocks_impl(nb200_ctx *ctx, const void *d_blocks, uint32_t n_blo
                                                                ctx->d_vote_gather.as<DeviceRun>(), d_total);
         NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
+        // nothing after this point reads d_blocks: whoever fills them may be told so
+        if (blocks_consumed) NB_TRY(blocks_consumed(consumed_arg));
         PhaseTimer pt(ctx, NB200_PHASE_VOTE);
         NB_TRY(vote_enqueue(ctx, ctx->d_vote_gather.as<DeviceRun>(), d_total, (uint32_t)total_cap, hash_duration_ns,
                             n_videos, pairs, n_pairs, params));
