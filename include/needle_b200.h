@@ -85,9 +85,10 @@ enum {
     NB200_OPT_FORCE_GENERAL_MATCH = 1,
     /* NB200_OPT_K1_VARIANT: which fingerprint FFT kernel runs (all: one warp per 4096-sample frame, at
      * most 32 complex values per lane; same hashes up to FP32 rounding order, >= 99.99 % identical
-     * frames; a tuning switch).  0 = the default (17).  17 = tensor-memory kernel: the parked half of
-     * a frame lives in TMEM (tcgen05.st / tcgen05.ld), 16 warps per SM, FMA-fused butterflies;
-     * 16 / 112 = the same with the first revision of the arithmetic, 16 / 12 warps per SM;
+     * frames; a tuning switch).  0 = the default (19).  16..19 = tensor-memory kernel, 16 warps per SM:
+     * the parked half of a frame lives in TMEM (tcgen05.st / tcgen05.ld); 17 adds FMA-fused butterflies
+     * and the conversion unit, 18 fetches odd-aligned frames rotated by one sample (aligned words), 19
+     * keeps the pass-2 and split twiddles in TMEM as well (one slot per warp); 112 = 16 with 12 warps;
      * 8, 10, 12 = the parked half in shared memory, that many warps per SM; 1 = all 64 values of a
      * lane in registers (8 warps per SM). */
     NB200_OPT_K1_VARIANT = 2,

@@ -209,7 +209,7 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
         return NB200_OK;
     case NB200_OPT_K1_VARIANT:
         if (value != 0 && value != 1 && value != 8 && value != 10 && value != 12 && value != 16 && value != 17 &&
-            value != 18 && value != 112)
+            value != 18 && value != 19 && value != 112)
             return NB200_ERR_INVALID_ARGUMENT;
         ctx->k1_variant = (int)value;
         return NB200_OK;

@@ -628,6 +628,11 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, f2 (&r)[4]) {
                  : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y)
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld4(f2 (&r)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(r[0].x), "+f"(r[0].y), "+f"(r[1].x), "+f"(r[1].y), "+f"(r[2].x), "+f"(r[2].y), "+f"(r[3].x), "+f"(r[3].y)
+                 :: "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld4x2(f2 (&r)[4], f2 (&q)[4]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(r[0].x), "+f"(r[0].y), "+f"(r[1].x), "+f"(r[1].y), "+f"(r[2].x), "+f"(r[2].y), "+f"(r[3].x), "+f"(r[3].y),
@@ -795,8 +800,42 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     // this warp's lanes (its quadrant of the 128) and its two 64-column slots
-    const uint32_t tA = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 128u;
-    const uint32_t tB = tA + 64u;
+    // REV >= 4: ONE 64-column slot per warp -- Y[k] leaves it for the exchange rows as soon as pass 2
+    // (q = 1) has pulled its rows into registers, before that pass's FFT, so the odd rows of Z can take
+    // the same columns afterwards.  The freed half of TMEM holds two lane-private constant tables in
+    // the order a lane reads them: the pass-2 twiddles (columns 256..383) and the split's
+    // W_4096^(L + 32 t) (384..465).  TMEM reads are ~20x what this kernel needs (tools/tmem_bw.cu);
+    // shared memory was its busiest pipe (73 % of peak wavefronts).
+    const uint32_t tq = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    const uint32_t tA = tq + (uint32_t)(warp >> 2) * (REV >= 4 ? 64u : 128u);
+    const uint32_t tB = REV >= 4 ? tA : tA + 64u;
+    const uint32_t tT = tq + 256u, tS = tq + 384u;
+    if (REV >= 4) {
+        if (warp < 4) {   // one warp per lane quadrant fills that quadrant's copy
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                f2 tv[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int t = 8 * c + e;                                   // table position
+                    const int hq = t >> 5, n1 = (t >> 2) & 7, i = t & 3;
+                    tv[e] = a.twiddle[(n1 + 8 * i) * 64 + lane + 32 * (1 - hq)];   // first q = 1 (hq = 0), then q = 0
+                }
+                tmem_st8(tT + 16 * c, tv[0], tv[1], tv[2], tv[3], tv[4], tv[5], tv[6], tv[7]);
+            }
+#pragma unroll 1
+            for (int c = 0; c < 6; c++) {
+                f2 sv8[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) sv8[e] = a.wsplit[min(8 * c + e, FP_T - 1) * 32 + lane];   // rows t = 8 c + e
+                tmem_st8(tS + 16 * c, sv8[0], sv8[1], sv8[2], sv8[3], sv8[4], sv8[5], sv8[6], sv8[7]);
+            }
+            tmem_wait_st();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
 
     f2 *xchg = reinterpret_cast<f2 *>(s_warp + warp * TM_WARP_BYTES);
     const uint32_t *pcm_words = reinterpret_cast<const uint32_t *>(xchg);
@@ -944,7 +983,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
         // ---- pass 2: k1 = L + 32 (q = 1: odd t, parked in slot B), then k1 = L (q = 0: even t, in registers)
 #pragma unroll 1
         for (int q = 1; q >= 0; q--) {
-            if (q == 0) {
+            if (q == 0 && REV < 4) {
                 // Y[k], k < 32, from slot A into the rows that pass q = 1 has consumed
                 tmem_wait_st();
 #pragma unroll
@@ -957,16 +996,25 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                 }
                 __syncwarp();
             }
+            if (q == 0 && REV >= 4) __syncwarp();   // the rows written after pass q = 1's reads are visible
             const f2 *row = xchg + lane * XCHG_STRIDE;
             const f2 *tw = s_twiddle + lane + 32 * q;
             if (REV >= 2) {
                 // twiddles and first radix-2 layer in one, scalar FFMA: c0 = r0 t0, c0 + r2 t2, 2 c0 - that
 #pragma unroll
                 for (int n1 = 0; n1 < 8; n1++) {
-                    const f2 c0 = n1 == 0 ? row[0] : cmul_s(row[n1], tw[n1 * 64]);
-                    const f2 c1 = cmul_s(row[n1 + 8], tw[(n1 + 8) * 64]);
-                    const f2 d0 = cmad_s(row[n1 + 16], tw[(n1 + 16) * 64], c0);
-                    const f2 d2 = cmad_s(row[n1 + 24], tw[(n1 + 24) * 64], c1);
+                    f2 t4[4];
+                    if (REV >= 4) {
+                        tmem_ld4(tT + 64 * (1 - q) + 8 * n1, t4);
+                        tmem_wait_ld4(t4);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) t4[i] = tw[(n1 + 8 * i) * 64];
+                    }
+                    const f2 c0 = n1 == 0 ? row[0] : cmul_s(row[n1], t4[0]);
+                    const f2 c1 = cmul_s(row[n1 + 8], t4[1]);
+                    const f2 d0 = cmad_s(row[n1 + 16], t4[2], c0);
+                    const f2 d2 = cmad_s(row[n1 + 24], t4[3], c1);
                     v[n1] = d0;
                     v[n1 + 16] = fma2(c0, make_float2(2.f, 2.f), neg2(d0));
                     v[n1 + 8] = d2;
@@ -977,6 +1025,18 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                 for (int n2 = 0; n2 < 32; n2++) v[n2] = cmul3(row[n2], tw[n2 * 64]);
             }
             __syncwarp();   // the rows are consumed
+            if (q == 1 && REV >= 4) {
+                // the rows are free and the FFT has not started: Y[k], k < 32, leaves the slot for them now
+                tmem_wait_st();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    f2 y[8];
+                    tmem_ld8(tA + 16 * c, y);
+                    tmem_wait_ld8(y);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) sts2(lane_addr + (c + 4 * i) * ROW, y[i]);
+                }
+            }
             if (q == 0) {
                 // the buffer is free: start the next frame's PCM on its way
                 const uint32_t nblk = blk + gridDim.x;
@@ -1011,10 +1071,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
         // partner value is the partner lane's entry; lane 0's partner of the odd row is its own)
 #pragma unroll
         for (int g = 0; g < 5; g++) {
-            f2 pa[4], pb[4];
+            f2 pa[4], pb[4], ws[8];
             tmem_ld4(tB + 2 * (4 * g), pa);          // entries 4 g .. 4 g + 3
             tmem_ld4(tB + 2 * (28 - 4 * g), pb);     // entries 28 - 4 g .. 31 - 4 g: pb[3 - i] = entry 31 - (4 g + i)
+            if (REV >= 4) tmem_ld8(tS + 16 * g, ws);  // W_4096^(L + 32 t), t = 8 g .. 8 g + 7
             tmem_wait_ld4x2(pa, pb);
+            if (REV >= 4) tmem_wait_ld8(ws);
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int a2 = 4 * g + i;
@@ -1025,7 +1087,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                     zp.x = __shfl_sync(0xffffffffu, pb[3 - i].x, partner);
                     zp.y = __shfl_sync(0xffffffffu, pb[3 - i].y, partner);
                     if (lane == 0) zp = own;
-                    if (REV >= 2) tm_bin2(2 * a2, z, zp, s_wsplit[(2 * a2) * 32 + lane], fold_m, acc); else tm_bin(2 * a2, z, zp, lw, fold_m, acc);
+                    if (REV >= 2) tm_bin2(2 * a2, z, zp, REV >= 4 ? ws[2 * i] : s_wsplit[(2 * a2) * 32 + lane], fold_m, acc); else tm_bin(2 * a2, z, zp, lw, fold_m, acc);
                 }
                 {   // t = 2 a + 1: own parked entry a; partner's register; lane 0: its own parked entry 31 - a
                     const f2 z = pa[i];
@@ -1034,7 +1096,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
                     zp.x = __shfl_sync(0xffffffffu, ps.x, partner);
                     zp.y = __shfl_sync(0xffffffffu, ps.y, partner);
                     if (lane == 0) zp = pb[3 - i];
-                    if (REV >= 2) tm_bin2(2 * a2 + 1, z, zp, s_wsplit[(2 * a2 + 1) * 32 + lane], fold_m, acc); else tm_bin(2 * a2 + 1, z, zp, lw, fold_m, acc);
+                    if (REV >= 2) tm_bin2(2 * a2 + 1, z, zp, REV >= 4 ? ws[2 * i + 1] : s_wsplit[(2 * a2 + 1) * 32 + lane], fold_m, acc); else tm_bin(2 * a2 + 1, z, zp, lw, fold_m, acc);
                 }
             }
         }
@@ -1046,7 +1108,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fp_fft_chroma_tm_kernel(const K1Ar
             zp.x = __shfl_sync(0xffffffffu, p11.x, partner);
             zp.y = __shfl_sync(0xffffffffu, p11.y, partner);
             if (lane == 0) zp = own;
-            if (REV >= 2) tm_bin2(40, z, zp, s_wsplit[40 * 32 + lane], fold_m, acc); else tm_bin(40, z, zp, lw, fold_m, acc);
+            if (REV >= 2) tm_bin2(40, z, zp, REV >= 4 ? tmem_ld1_wait(tS + 80) : s_wsplit[40 * 32 + lane], fold_m, acc); else tm_bin(40, z, zp, lw, fold_m, acc);
         }
         // 12 sums over 32 lanes with halving butterflies (as in the h32 kernel): 18 shuffles
         float r6[6], r3[3];
@@ -1330,6 +1392,8 @@ static int ensure_fp_tables(nb200_ctx *ctx) {
                                  tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<16>()));
+    NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tm_smem_bytes<16>()));
     NB_CUDA(cudaFuncSetAttribute(fp_fft_chroma_tm_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tm_smem_bytes<12>()));
     ctx->fp_ready = true;
@@ -1442,14 +1506,16 @@ static int fingerprint_run_pipelined(nb200_ctx *ctx, const nb200_pcmset *ps, con
         auto launch_k1 = [&](uint32_t f0, uint32_t f1) -> cudaError_t {
             if (f1 <= f0) return cudaSuccess;
             const uint32_t nf = f1 - f0;
-            const int variant = ctx->k1_variant == 0 ? 18 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM, revision-2 arithmetic
+            const int variant = ctx->k1_variant == 0 ? 19 : ctx->k1_variant;   // default: tensor-memory kernel, 16 warps per SM, revision 4
             if (variant >= 16) {
                 // tensor-memory kernel: 16 (or, variant 112, 12) warps per SM
                 k1.frame_begin = f0;
                 k1.frame_end = f1;
                 const uint32_t nw = variant == 112 ? 12u : 16u;
                 const uint32_t grid1 = std::min<uint32_t>((uint32_t)ctx->sm_count, (nf + nw - 1) / nw);
-                if (variant == 18)
+                if (variant == 19)
+                    fp_fft_chroma_tm_kernel<16, 4><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
+                else if (variant == 18)
                     fp_fft_chroma_tm_kernel<16, 3><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);
                 else if (variant == 17)
                     fp_fft_chroma_tm_kernel<16, 2><<<grid1, 16 * 32, tm_smem_bytes<16>(), st>>>(k1);

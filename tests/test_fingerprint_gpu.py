@@ -32,7 +32,7 @@ def make_pcm(seed, seconds, kind="mix"):
     return np.clip(np.rint(x * 32767.0), -32768, 32767).astype(np.int16)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 8, 12, 16, 112])
+@pytest.mark.parametrize("variant", [0, 1, 8, 12, 16, 17, 18, 112])
 @pytest.mark.parametrize("kind", ["noise", "chords", "mix"])
 def test_raw_hashes_match_oracle(ctx, oracle, kind, variant):
     """Every K1 kernel variant (NB200_OPT_K1_VARIANT: 0 = the default tensor-memory kernel; 16/112 its

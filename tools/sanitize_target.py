@@ -10,7 +10,7 @@ rng = np.random.default_rng(0)
 lens = [0, 4095, 4096, 4096 + 1365 * 19, 4096 + 1365 * 40 + 7, 60_001, 90_000, 33_333]
 segs = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
 ref = None
-for variant in (0, 1, 8, 10, 12, 16, 112):
+for variant in (0, 1, 8, 10, 12, 16, 17, 18, 112):
     ctx.set_option(2, variant)
     out = ctx.fingerprint_batch(segs)
     if ref is None:
