@@ -566,7 +566,15 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     sm_mhz = clocks["sm_mhz"] or SM_MHZ_MAX
-    fp32_peak = SM_COUNT * FP32_LANE_OPS_PER_CLK_PER_SM * 2 * SM_MHZ_MAX * 1e6 / 1e12
+    lane_ops, lane_src = FP32_LANE_OPS_PER_CLK_PER_SM, "profiles/r02_k1_fp_mix_peak.jsonl"
+    try:   # the measurement for the current kernel's mix, when it has been taken on this pool
+        for ln in open(os.path.join(ROOT, "profiles", "r02_k1_fp_mix_peak_v4.jsonl")):
+            rec = json.loads(ln)
+            if rec.get("test", "").startswith("k1 fp mix, revision-4"):
+                lane_ops, lane_src = float(rec["fp32_lane_ops_per_clk_per_sm"]), "profiles/r02_k1_fp_mix_peak_v4.jsonl"
+    except Exception:
+        pass
+    fp32_peak = SM_COUNT * lane_ops * 2 * SM_MHZ_MAX * 1e6 / 1e12
     popc_peak = SM_COUNT * POPC_PER_CLK_PER_SM * SM_MHZ_MAX * 1e6 / 1e12
     traffic_per_frame, traffic_src = None, None
     try:
@@ -626,8 +634,8 @@ def run_b200(args):
             "kernel": "fp_fft_chroma_tm_kernel (K1) of the fingerprint leg: the kernel with the largest share of this run's GPU time",
             "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fp32_peak, "frac": achieved / fp32_peak,
             "peak_source": "MEASURED: K1's own FP32 instruction mix with no memory or integer work reaches %.1f results per "
-                           "clock per SM (tools/k1_mix_peak.cu, profiles/r02_k1_fp_mix_peak.jsonl; nominal 128) x 2 flop "
-                           "x 148 SM x 1965 MHz" % FP32_LANE_OPS_PER_CLK_PER_SM,
+                           "clock per SM (tools/k1_mix_peak.cu, %s; nominal 128) x 2 flop "
+                           "x 148 SM x 1965 MHz" % (lane_ops, lane_src),
             "frac_of_nominal_74p4": achieved / (SM_COUNT * 128 * 2 * SM_MHZ_MAX * 1e6 / 1e12),
             "frames_per_launch": fp["frames_local"], "flop_per_frame": FLOP_PER_FRAME, "kernel_ms": fp["k1_ms"],
             "traffic": (traffic_per_frame * fp["frames_local"]) if traffic_per_frame else None, "traffic_source": traffic_src,

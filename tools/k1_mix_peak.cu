@@ -15,8 +15,10 @@
 #include <cuda_runtime.h>
 
 constexpr int CHAINS = 16;
-constexpr int UNIT_A2 = 13, UNIT_F2 = 11, UNIT_M2 = 9;   // packed ops per unit (649 : 535 : 462)
+constexpr int UNIT_A2 = 13, UNIT_F2 = 11, UNIT_M2 = 9;   // packed ops per unit (649 : 535 : 462): round 1's h32 kernel
 constexpr int UNIT_A1 = 4, UNIT_M1 = 1, UNIT_F1 = 1;     // scalar ops per unit (189 : 53 : 41 + part of the rest)
+// the mix of the current default kernel (revision 4: 258 FADD2, 639 FFMA2, 100 FMUL2, 128 FADD, 104 FMUL, 393 FFMA)
+constexpr int V4_A2 = 5, V4_F2 = 13, V4_M2 = 2, V4_A1 = 3, V4_M1 = 2, V4_F1 = 8;
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk(float a, float b) { return ((u64)__float_as_uint(b) << 32) | __float_as_uint(a); }
@@ -56,6 +58,18 @@ __global__ void __launch_bounds__(512, 1) mix_kernel(float2 *out, int iters, flo
                 if (r < UNIT_A1) { a1(y[d], sa); d++; }
                 if (r == 5) { m1(y[d], sm); d++; }
                 if (r == 7) { f1(y[d], sm, sa); d++; }
+            }
+        } else if (MODE == 5) {
+            // 20 packed + 13 scalar ops in the proportions of the revision-4 kernel; chains 0-3 add, 4-12 fma, 13-15 mul
+            int ca_ = 0, cf_ = 0, cm_ = 0, d = 0;
+#pragma unroll
+            for (int r = 0; r < V4_F2; r++) {
+                f2(x[4 + cf_], cf, ca); cf_ = (cf_ + 1) % 9;
+                if (r < V4_A2) { a2(x[ca_], ca); ca_ = (ca_ + 1) % 4; }
+                if (r < V4_M2) { m2(x[13 + cm_], cm); cm_ = (cm_ + 1) % 3; }
+                if (r < V4_F1) { f1(y[d], sm, sa); d++; }
+                if (r < V4_A1) { a1(y[d], sa); d++; }
+                if (r < V4_M1) { m1(y[d], sm); d++; }
             }
         } else {
 #pragma unroll
@@ -122,6 +136,18 @@ int main(int argc, char **argv) {
                ms, packed_frame, scalar_frame, frame_cycles, frames_per_s, clock_khz / 1000,
                pipe_cycles_per_s / (sms * 4.0) / (clock_khz * 1e3),
                pipe_cycles_per_s * 32.0 / sms / (clock_khz * 1e3));
+    }
+    {
+        const double ms = time_ms<5>(sms, iters, out);
+        const double unit_cycles = 2.0 * (V4_A2 + V4_F2 + V4_M2) + (V4_A1 + V4_M1 + V4_F1);
+        const double frame_cycles = 2.0 * (258 + 639 + 100) + (128 + 104 + 393);
+        const double units_per_s = warps * iters / (ms * 1e-3);
+        const double pipe_cycles_per_s = units_per_s * unit_cycles;
+        printf("{\"test\": \"k1 fp mix, revision-4 kernel\", \"ms\": %.4f, \"packed_per_frame\": 997, \"scalar_per_frame\": 625, "
+               "\"fma_pipe_cycles_per_frame_warp\": %.0f, \"frames_per_s_ceiling\": %.4e, "
+               "\"pipe_cycles_per_clk_per_scheduler_at_%d_MHz\": %.4f, \"fp32_lane_ops_per_clk_per_sm\": %.2f}\n",
+               ms, frame_cycles, units_per_s * unit_cycles / frame_cycles, clock_khz / 1000,
+               pipe_cycles_per_s / (sms * 4.0) / (clock_khz * 1e3), pipe_cycles_per_s * 32.0 / sms / (clock_khz * 1e3));
     }
     const char *names[] = {"", "fadd2 only", "ffma2 only", "ffma scalar only", "ffma2 + ffma alternating"};
     double msv[5];
