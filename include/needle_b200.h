@@ -220,6 +220,12 @@ int nb200_vote_subset(const uint64_t *hash_duration_ns, uint32_t n_videos, const
 
 /* ------------------------------------------ device-resident staged pipeline */
 
+/* A season from host arrays (layout as for nb200_match_pairs).  The caller's arrays are free again when
+ * the call returns; the copies themselves are left to the context's stream.  Page-locked arrays
+ * (nb200_host_alloc, cudaHostAlloc, cudaHostRegister) are copied from directly -- two contiguous H2D
+ * copies and a device-side move into the aligned layout; ordinary memory is staged through the
+ * library's own pinned area first (about 1 ms per 10 MB).  nb200_search / nb200_match_pairs take the
+ * same route for their inputs. */
 int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
                          const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out);
 /* Sizes: total = number of hashes; seg_offset_out[2*n_videos+1] (may be NULL). */

@@ -162,7 +162,8 @@ struct MatchPlanCache {
     uint64_t key = 0;
     uint64_t data_uid = 0;   // immutable hashset whose bounds and repeated lists the arena / d_dst2 hold (0: none)
     uint32_t n_problems = 0, d2_max = 1, max_len = 1;
-    uint64_t tiles_f = 0, tiles_g = 0, cells = 0, d2_total = 0;
+    uint64_t tiles_f = 0, tiles_g = 0, cells = 0, d2_total = 0;   // tiles_f counts the fast kernel's units
+    uint32_t band_group = 1;
     size_t o_tab = 0, o_lmin = 0, o_d2 = 0, o_prob_f = 0, o_tend_f = 0, o_lut_f = 0, o_prob_g = 0, o_tend_g = 0, o_lut_g = 0;
     std::vector<uint32_t> problem_pair;
     std::vector<uint8_t> problem_is_ending;
@@ -176,10 +177,10 @@ struct nb200_ctx {
     cudaStream_t stream = nullptr;     // the one in use (own or caller's)
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[10] = {};           // pairs: K1, K2, K3, K4, device vote
-    cudaEvent_t ev_chunk[12] = {};     // [0..5] H2D chunk landed (pipelined analyze), [6] tsfill, [7] PCM guard,
+    cudaEvent_t ev_chunk[13] = {};     // [0..5] H2D chunk landed (pipelined analyze), [6] tsfill, [7] PCM guard,
                                        // [8] match descriptors landed, [9] vote descriptors landed,
                                        // [10] the last enqueued match stage (arena + staging readers) is done,
-                                       // [11] the last enqueued fingerprint stage is done
+                                       // [11] the last enqueued fingerprint stage is done, [12] hashset upload staging drained
     bool ev_valid[5] = {false, false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
@@ -193,6 +194,8 @@ struct nb200_ctx {
     nb200::MatchPlanCache match_plan;   // what that arena currently holds
     nb200::DevBuf d_counters, d_runs, d_dst2;   // d_dst2: the fast match kernel's repeated dst lists
     nb200::PinnedBuf h_stage, h_small, h_runs, h_tsfill;
+    nb200::PinnedBuf h_upload;   // nb200_hashset_upload's staging area (guarded by ev_chunk[12])
+    nb200::DevBuf d_upload;      // ... and its device scratch for page-locked input (packed arrays + offset tables)
     nb200::PinnedBuf h_fp_stage, h_vote_stage, h_results;   // one staging area per phase: nothing waits for a copy to drain
     // device vote scratch (vote_device.cu)
     nb200::DevBuf d_vote_groups, d_vote_order, d_vote_csr, d_vote_hd, d_vote_results, d_vote_flags, d_vote_scan_tmp,

@@ -62,6 +62,7 @@ struct MatchProblem {
     // fast kernel: the dst list's live columns 1 .. m-1, padded to `period` (a multiple of 4) and
     // repeated, so that every wrapped 512-column window is ONE 16-byte-aligned span (dst2_build_kernel)
     uint32_t dst2_off, period;
+    uint32_t n_groups;      // fast kernel: units (band groups) per row chunk; tile_begin counts units
 };
 
 struct MatchArgs {
@@ -71,7 +72,8 @@ struct MatchArgs {
     const uint32_t *tile_end;   // [n_problems] exclusive end tile id per problem
     const uint32_t *lut;        // [n_tiles >> LUT_SHIFT + 1] first problem whose tile_end > (k << LUT_SHIFT)
     const uint32_t *dst2;       // fast kernel: repeated live columns of every list (MatchProblem::dst2_off)
-    uint32_t n_tiles;
+    uint32_t n_tiles;           // work items under the cursor: tiles (general kernel) or units (fast kernel)
+    uint32_t band_group;        // fast kernel: bands per unit
     uint32_t threshold;
     uint32_t run_cap;
     // 0: run; 1: run iff every problem's lcand >= 63 (the fast kernel's precondition);
@@ -88,6 +90,13 @@ __device__ __forceinline__ bool not_my_turn(const MatchArgs &a) {
     if (a.mode == 0) return false;
     const uint32_t min_lcand = ~a.counters[3];
     return (a.mode == 1) != (min_lcand >= FAST_MIN_LCAND);
+}
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
 }
 
 __device__ __forceinline__ bool hamming_match(uint32_t a, uint32_t b, uint32_t T) {
@@ -374,6 +383,38 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_kernel(const MatchA
     }
 }
 
+// The adaptive fast kernel's first look at a 32-row word: per lane, the smallest sum of Hamming distances
+// over rows 0, 12, 24 among its 8 diagonals.  dl = the lane's dst window of the word, sp = the word's src rows.
+__device__ __forceinline__ int first_look(const uint32_t *dl, const uint32_t *sp) {
+    const uint4 *dptr = reinterpret_cast<const uint4 *>(dl);
+    uint32_t pw[24];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        const uint4 v0 = dptr[3 * g], v1 = dptr[3 * g + 1];
+        pw[8 * g + 0] = v0.x;
+        pw[8 * g + 1] = v0.y;
+        pw[8 * g + 2] = v0.z;
+        pw[8 * g + 3] = v0.w;
+        pw[8 * g + 4] = v1.x;
+        pw[8 * g + 5] = v1.y;
+        pw[8 * g + 6] = v1.z;
+        pw[8 * g + 7] = v1.w;
+    }
+    const uint32_t s0 = sp[0], s1 = sp[12], s2 = sp[24];
+    const uint32_t s01 = s0 ^ s1;
+    int lo = 1 << 20;
+#pragma unroll
+    for (int c = 0; c < MATCH_C; c++) {
+        // x_k = s_k ^ d_k;  t = x0 ^ x1;  ones = t ^ x2;  twos = maj(x0, x1, x2) = t ? ~ones : x0
+        const uint32_t d0 = pw[(MATCH_C - 1) - c], d1 = pw[8 + (MATCH_C - 1) - c], d2 = pw[16 + (MATCH_C - 1) - c];
+        const uint32_t t = lop3<0x96>(d0, d1, s01);
+        const uint32_t ones = lop3<0x96>(t, d2, s2);
+        const uint32_t twos = lop3<0x74>(d0 ^ s0, t, ones);
+        lo = min(lo, __popc(ones) + 2 * __popc(twos));
+    }
+    return lo;
+}
+
 // ---------------------------------------------------------------------------
 // Fast variant for lcand >= 63 (every default configuration: 20 s / 0.246 s = 82
 // cells).  A run that long contains at least one ALIGNED 32-row word of its
@@ -476,6 +517,11 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
     // two tile buffers per warp: the next tile's hashes arrive by bulk copy (TMA) while this one is matched
     __shared__ __align__(128) uint32_t s_src[MATCH_WARPS][2][MATCH_R];
     __shared__ __align__(128) uint32_t s_dst[MATCH_WARPS][2][FAST_DST_TILE];
+    // A second copy of the dst window, 16 bytes further into its 128-byte line.  A lane's 16-byte loads
+    // are 32 bytes from its neighbour's, so the 8 lanes of one wavefront would cover only 4 of the 8
+    // 16-byte bank groups twice (r02_ncu_k3_final.txt: 11.6 M conflict wavefronts, the LSU data pipe at
+    // 73 %); lanes with bit 2 set read this copy and land on the other 4 groups.
+    __shared__ __align__(128) uint32_t s_dst_b[MATCH_WARPS][2][FAST_DST_TILE + 32];
     __shared__ __align__(8) uint64_t s_bar[MATCH_WARPS][2];
 
     const int lane = threadIdx.x & 31;
@@ -494,63 +540,120 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
     // the dst window of a tile then starts at a multiple of 4 elements (r0, ub and 256 are), i.e. 16-byte
     // aligned in the repeated list a.dst2 -- one bulk copy.  Columns M .. Mp-1 are padding: a word that
     // touches them is rejected where full words are reported, like the wrap point.
-    struct Tile {
+    //
+    // What a warp claims from the global cursor is a UNIT: one row chunk x up to a.band_group consecutive
+    // bands (tiles) of one problem.  The atomic, the LUT walk, the descriptor loads and the divisions --
+    // a chain of dependent L2 round trips, a third of the kernel's stall samples when paid per tile
+    // (profiles/r02_ncu_k3_v2.txt) -- are paid once per unit; the src rows are fetched once per unit;
+    // from band to band only the dst window moves, by 256 columns.
+    struct Unit {
         uint32_t p;
-        int n, M, Mp, r0, ub;
+        int n, M, Mp, r0, ub0, nb, e0, estep;
     };
-    auto claim = [&](Tile &t) -> bool {   // next tile from the global cursor + its bulk copies into buffer b
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&a.counters[0], 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.n_tiles) return false;
-        uint32_t p = a.lut[tile >> LUT_SHIFT];
-        while (tile >= a.tile_end[p]) p++;
+    auto claim = [&](Unit &t) -> bool {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(&a.counters[0], 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= a.n_tiles) return false;
+        uint32_t p = a.lut[unit >> LUT_SHIFT];
+        while (unit >= a.tile_end[p]) p++;
         const MatchProblem &pr = a.problems[p];
-        const uint32_t local = tile - pr.tile_begin;
-        const int chunk = (int)(local / pr.n_bands);
+        const uint32_t local = unit - pr.tile_begin;
+        const uint32_t chunk = local / pr.n_groups;
+        const uint32_t band0 = (local - chunk * pr.n_groups) * a.band_group;
         t.p = p;
         t.n = (int)pr.n;
         t.M = (int)pr.m - 1;
         t.Mp = (int)pr.period;
-        t.r0 = chunk * MATCH_R;
-        t.ub = (int)(local - (uint32_t)chunk * pr.n_bands) * MATCH_DW;
+        t.r0 = (int)chunk * MATCH_R;
+        t.ub0 = (int)band0 * MATCH_DW;
+        t.nb = (int)min(a.band_group, pr.n_bands - band0);
+        // dst_t[s] = column 1 + ((e + s) mod Mp) of dst,  cell (row r0+kk, diagonal ub+x) <-> s = 255 + kk - x
+        int e0 = (t.r0 - t.ub0 - MATCH_DW) % t.Mp;
+        if (e0 < 0) e0 += t.Mp;
+        t.e0 = e0;
+        t.estep = MATCH_DW % t.Mp;     // e of the next band = e - 256 (mod Mp)
         return true;
     };
-    auto fetch = [&](const Tile &t, int b) {
+    // bulk copies of one tile into dst buffer b: its dst window (twice, see s_dst_b) and, at the first
+    // band of a unit, the unit's src rows into src buffer sb
+    auto fetch = [&](const Unit &t, int e, int b, int sb, bool with_src) {
         const MatchProblem &pr = a.problems[t.p];
-        // dst_t[s] = column 1 + ((e0 + s) mod Mp) of dst,  cell (row r0+kk, diagonal ub+x) <-> s = 255 + kk - x
-        int e0 = (t.r0 - t.ub - MATCH_DW) % t.Mp;
-        if (e0 < 0) e0 += t.Mp;
         const uint32_t *hs = a.hashes + pr.src_off + t.r0;
-        const int rows = min(MATCH_R, t.n - t.r0), sn = rows & ~3;   // rows past n are never used unmasked
+        const int rows = min(MATCH_R, t.n - t.r0), sn = with_src ? (rows & ~3) : 0;   // rows past n are never used unmasked
         fence_proxy_async();
         if (lane == 0) {
             const uint32_t bar = smem_u32(&s_bar[warp][b]);
-            mbar_expect_tx(bar, (uint32_t)sn * 4u + FAST_DST_TILE * 4u);
-            if (sn) bulk_g2s(smem_u32(&s_src[warp][b][0]), hs, (uint32_t)sn * 4u, bar);
-            bulk_g2s(smem_u32(&s_dst[warp][b][0]), a.dst2 + pr.dst2_off + e0, FAST_DST_TILE * 4u, bar);
+            mbar_expect_tx(bar, (uint32_t)sn * 4u + 2u * FAST_DST_TILE * 4u);
+            if (sn) bulk_g2s(smem_u32(&s_src[warp][sb][0]), hs, (uint32_t)sn * 4u, bar);
+            bulk_g2s(smem_u32(&s_dst[warp][b][0]), a.dst2 + pr.dst2_off + e, FAST_DST_TILE * 4u, bar);
+            bulk_g2s(smem_u32(&s_dst_b[warp][b][4]), a.dst2 + pr.dst2_off + e, FAST_DST_TILE * 4u, bar);
         }
-        if (lane < 3 && sn + lane < rows) s_src[warp][b][sn + lane] = hs[sn + lane];   // a list need not end on 16 bytes
+        if (with_src && lane < 3 && sn + lane < rows) s_src[warp][sb][sn + lane] = hs[sn + lane];   // a list need not end on 16 bytes
     };
 
-    Tile cur, nxt;
+    Unit cur, nxt;
     bool have = claim(cur);
-    if (have) fetch(cur, 0);
+    int band = 0, sb = 0, e_cur = 0;   // band of the unit being matched; its src buffer; e of the last window fetched
+    if (have) {
+        e_cur = cur.e0;
+        fetch(cur, e_cur, 0, 0, true);
+    }
     uint32_t phase[2] = {0u, 0u};
     for (int buf = 0; have; buf ^= 1) {
-        const bool have_next = claim(nxt);
-        if (have_next) fetch(nxt, buf ^ 1);   // that buffer's last readers finished before the __syncwarp below
+        // the tile after this one: the unit's next band, or the first band of the next unit
+        const bool same_unit = band + 1 < cur.nb;
+        bool have_next = true;
+        if (same_unit) {
+            e_cur -= cur.estep;
+            if (e_cur < 0) e_cur += cur.Mp;
+            fetch(cur, e_cur, buf ^ 1, sb, false);   // that buffer's last readers finished before the __syncwarp below
+        } else {
+            have_next = claim(nxt);
+            if (have_next) {
+                e_cur = nxt.e0;
+                fetch(nxt, e_cur, buf ^ 1, sb ^ 1, true);
+            }
+        }
         mbar_wait(smem_u32(&s_bar[warp][buf]), phase[buf]);
         phase[buf] ^= 1;
         __syncwarp();
-        const uint32_t *src_t = s_src[warp][buf];
+        const uint32_t *src_t = s_src[warp][sb];
         const uint32_t *dst_t = s_dst[warp][buf];
+        const uint32_t *dst_l = (lane & 4) ? &s_dst_b[warp][buf][4] : dst_t;   // this lane's copy (bank groups)
         const uint32_t p = cur.p;
-        const int n = cur.n, M = cur.M, Mp = cur.Mp, r0 = cur.r0, ub = cur.ub;
+        const int n = cur.n, M = cur.M, Mp = cur.Mp, r0 = cur.r0, ub = cur.ub0 + band * MATCH_DW;
 
         const int n_steps = min(MATCH_R / 32, (n - r0 + 31) / 32);
-        for (int step = 0; step < n_steps; step++) {
-            const uint4 *dptr = reinterpret_cast<const uint4 *>(dst_t + (248 + 32 * step - MATCH_C * lane));
+        int pf_score = 3;   // two words in a row must survive the first look before it is switched off
+        const uint32_t *dl0 = dst_l + (248 - MATCH_C * lane);
+        for (int step2 = 0; step2 < n_steps; step2 += 2) {
+          // words are taken two at a time: two independent chains through the first look
+          uint32_t todo = step2 + 1 < n_steps ? 3u : 1u;
+          if (SAMPLED && pf_score > 0) {
+              // First look, 2 POPCs for 3 cells of a diagonal (rows 0, 12, 24 of the word): if all three
+              // match, their distances add up to at most 3 T.  The three XOR words go through one
+              // carry-save adder -- ones = x0^x1^x2, twos = maj(x0,x1,x2), 4 LOP3 on the ALU pipe per diagonal --
+              // and sum = popc(ones) + 2 popc(twos).  Unrelated hashes (sum ~ 48 +- 4.9 against 3 T = 30)
+              // leave here at half the POPCs and 6 of the 10 window loads of the first 4-row stage.
+              // Exact: a word that fails cannot be full.  pf_score turns the look off while it is not
+              // paying (stationary audio, silence) and probes again at every tile.  (The second word of
+              // an odd tail is computed on whatever the buffers hold and ignored.)
+              const int lo0 = first_look(dl0 + 32 * step2, src_t + 32 * step2);
+              const int lo1 = first_look(dl0 + 32 * step2 + 32, src_t + 32 * step2 + 32);
+              // (handing the few surviving diagonals straight to coop_verify instead of the staged test was
+              // measured slower: 4.82 -> 5.51 ms on configs[3] -- a serial chain per survivor, 127 registers)
+              uint32_t surv = (__ballot_sync(0xffffffffu, lo0 <= 3 * T) ? 1u : 0u) |
+                              (__ballot_sync(0xffffffffu, lo1 <= 3 * T) ? 2u : 0u);
+              surv &= todo;
+              pf_score = min(pf_score + __popc(todo ^ surv) - 2 * __popc(surv), 8);
+              todo = surv;
+          }
+#pragma unroll 1
+          for (int w = 0; w < 2; w++) {
+            if (((todo >> w) & 1u) == 0) continue;
+            const int step = step2 + w;
+            const uint4 *dptr = reinterpret_cast<const uint4 *>(dl0 + 32 * step);
             int mx[MATCH_C];
 #pragma unroll
             for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
@@ -585,19 +688,8 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                                 const int p1 = __popc(sr[r + 1] ^ dw[o + 8 * (r + 1) + (MATCH_C - 1) - c]);
                                 mx[c] = max(mx[c], max(p0, p1));
                             }
-                            if (stage == 0 && r == 0) {
-                                // the very first look is at 2 rows only: unrelated hashes (p^2 ~ 6e-4 per
-                                // diagonal) leave 85 % of the words right here, at 16 POPCs per lane instead of 32
-                                int b1 = mx[0];
-#pragma unroll
-                                for (int c = 1; c < MATCH_C; c++) b1 = min(b1, mx[c]);
-                                if (__ballot_sync(0xffffffffu, b1 <= T) == 0) {
-                                    alive = false;
-                                    break;
-                                }
-                            }
                         }
-                        if (stage < 7 && alive) {
+                        if (stage < 7) {
                             int b2 = mx[0];
 #pragma unroll
                             for (int c = 1; c < MATCH_C; c++) b2 = min(b2, mx[c]);
@@ -662,10 +754,17 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const M
                     full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, Mp, M, n, lane);
                 }
             }
+          }
         }
         __syncwarp();   // every lane is done with this buffer: the tile after next may land in it
-        cur = nxt;
-        have = have_next;
+        if (same_unit) {
+            band++;
+        } else {
+            cur = nxt;
+            band = 0;
+            sb ^= 1;
+            have = have_next;
+        }
     }
 }
 
@@ -880,6 +979,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
                 cells += (uint64_t)n * m;
                 if (n < 2 || m < 2) continue;   // rows/cols 0 never match: no run possible (:165-167,179)
                 MatchProblem pr;
+                pr.n_groups = 0;
                 pr.src_off = hs->dev_offset[sa];
                 pr.n = n;
                 pr.dst_off = hs->dev_offset[sb];
@@ -905,6 +1005,21 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
                 pc.problem_pair.push_back((uint32_t)k);
                 pc.problem_is_ending.push_back((uint8_t)e);
             }
+        }
+        // fast kernel: bands are claimed in groups (units) so that the per-claim work is amortised, but
+        // never so large that a persistent warp gets fewer than ~12 units
+        {
+            const uint64_t warps = (uint64_t)ctx->sm_count * 4 * MATCH_WARPS;
+            const uint32_t G = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, tiles_f / (warps * 12)));
+            uint64_t units = 0;
+            for (MatchProblem &pr : prob_f) {
+                const uint64_t chunks = (pr.n + MATCH_R - 1) / MATCH_R;
+                pr.n_groups = (pr.n_bands + G - 1) / G;
+                pr.tile_begin = (uint32_t)units;
+                units += chunks * pr.n_groups;
+            }
+            tiles_f = units;
+            pc.band_group = G;
         }
         pc.cells = cells;
         pc.n_problems = (uint32_t)prob_f.size();
@@ -1033,6 +1148,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     }
 
     MatchArgs args;
+    args.band_group = 1;
     args.hashes = hs->d_hashes.as<uint32_t>();
     args.ts = hs->d_ts.as<uint64_t>();
     args.threshold = params->hash_match_threshold;
@@ -1058,6 +1174,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         args.tile_end = reinterpret_cast<const uint32_t *>(arena + o_tend_f);
         args.lut = reinterpret_cast<const uint32_t *>(arena + o_lut_f);
         args.n_tiles = (uint32_t)tiles_f;
+        args.band_group = pc.band_group;
         args.mode = 1;
         if (ctx->match_dense)
             match_fast_kernel<false><<<grid_for(tiles_f), MATCH_WARPS * 32, 0, s>>>(args);

@@ -42,6 +42,22 @@ def check_season(ctx, orc, season, vote=True, **kw):
     assert n_runs == len(want_rows)
     assert n_cells == season.n_cells(kw["include_endings"])
     assert np.array_equal(rs.download(), runs)
+    # page-locked input takes the direct route (two packed copies + a device-side move into the aligned layout)
+    pin_h = engine.PinnedArray.empty(season.hashes.size, np.uint32)
+    pin_t = engine.PinnedArray.empty(season.ts_ns.size, np.uint64)
+    try:
+        pin_h.array[:] = season.hashes
+        pin_t.array[:] = season.ts_ns
+        assert np.array_equal(ctx.match_pairs(pin_h.array, pin_t.array, season.seg_offset, p), runs)
+        hp = engine.HashSet.upload(ctx, pin_h.array, pin_t.array, season.seg_offset)
+        pin_h.array[:] = 0     # the upload has released the caller's arrays
+        pin_t.array[:] = 0
+        got_h, got_t, _off = hp.download()
+        assert np.array_equal(got_h, season.hashes) and np.array_equal(got_t, season.ts_ns)
+        hp.free()
+    finally:
+        pin_h.free()
+        pin_t.free()
     if vote:
         assert ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, p) == want_results
         assert hs.search(season.hash_duration_ns, p) == want_results       # device vote (vote_device.cu)
