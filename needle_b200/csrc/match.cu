@@ -513,7 +513,7 @@ __device__ __noinline__ void coop_verify(const EmitCtx ectx, uint32_t p, const u
 // warp) as soon as no diagonal survives -- usually after the first 4 rows, 1/8 of the
 // POPCs.  Survivors of all 8 stages are exactly the full words.  Same runs, bit for bit.
 template <bool SAMPLED>
-__global__ void __launch_bounds__(MATCH_WARPS * 32, 4) match_fast_kernel(const MatchArgs a) {
+__global__ void __launch_bounds__(MATCH_WARPS * 32, SAMPLED ? 5 : 4) match_fast_kernel(const MatchArgs a) {
     // two tile buffers per warp: the next tile's hashes arrive by bulk copy (TMA) while this one is matched
     __shared__ __align__(128) uint32_t s_src[MATCH_WARPS][2][MATCH_R];
     __shared__ __align__(128) uint32_t s_dst[MATCH_WARPS][2][FAST_DST_TILE];
@@ -1009,7 +1009,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         // fast kernel: bands are claimed in groups (units) so that the per-claim work is amortised, but
         // never so large that a persistent warp gets fewer than ~12 units
         {
-            const uint64_t warps = (uint64_t)ctx->sm_count * 4 * MATCH_WARPS;
+            const uint64_t warps = (uint64_t)ctx->sm_count * 5 * MATCH_WARPS;
             const uint32_t G = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, tiles_f / (warps * 12)));
             uint64_t units = 0;
             for (MatchProblem &pr : prob_f) {
@@ -1155,8 +1155,8 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     args.run_cap = run_cap;
     args.counters = ctx->d_counters.as<unsigned int>();
     args.runs = runs_out;
-    auto grid_for = [&](uint64_t n_tiles) {
-        return std::min<uint32_t>((uint32_t)ctx->sm_count * 4, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
+    auto grid_for = [&](uint64_t n_tiles, uint32_t ctas_per_sm = 4) {
+        return std::min<uint32_t>((uint32_t)ctx->sm_count * ctas_per_sm, (uint32_t)((n_tiles + MATCH_WARPS - 1) / MATCH_WARPS));
     };
     if (want_fast && !same_data) {
         // the repeated dst lists (a few MB at most): rebuilt with every match unless the season is the
@@ -1179,7 +1179,7 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         if (ctx->match_dense)
             match_fast_kernel<false><<<grid_for(tiles_f), MATCH_WARPS * 32, 0, s>>>(args);
         else
-            match_fast_kernel<true><<<grid_for(tiles_f), MATCH_WARPS * 32, 0, s>>>(args);
+            match_fast_kernel<true><<<grid_for(tiles_f, 5), MATCH_WARPS * 32, 0, s>>>(args);   // 96 registers, 41 KB: 5 CTAs per SM
         NB_CUDA(cudaGetLastError());
         ctx->n_launches++;
     }
