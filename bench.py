@@ -76,6 +76,18 @@ def parse_args():
 
 # ------------------------------------------------------------------ workloads
 
+def ncu_metric(path, name):
+    """One number out of a committed ncu summary (tools/ncu_summary.py format); None if absent."""
+    try:
+        for ln in open(os.path.join(os.path.dirname(os.path.abspath(__file__)), path)):
+            f = ln.split()
+            if len(f) >= 2 and f[0] == name:
+                return float(f[1])
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def search_season():
     """configs[3]: uniform random hashes, a shared run of 366 hashes (90 s) planted in every
     opening and ending list with bit flips and hard breaks."""
@@ -630,8 +642,10 @@ def run_b200(args):
         "kernel_ms": dense_ms, "cells_per_launch": cells // world,
         "peak": popc_peak, "peak_source": "MEASURED POPC issue rate %.1f/clk/SM (tools/pipe_peak.cu, "
                                           "profiles/r01_pipe_peak_warm.jsonl; nominal 16) x 148 SM x 1965 MHz" % POPC_PER_CLK_PER_SM,
-        "default_kernel": "match_fast_kernel<adaptive>: tests 4 rows of each 32-row word per stage and leaves when no "
-                          "diagonal survives -- fewer POPCs than cells, identical runs (tests/test_match_gpu.py)",
+        "default_kernel": "match_fast_kernel<adaptive>: a first look at 3 rows of each 32-row word (2 POPCs through a carry-save "
+                          "adder), then 4 rows per stage; leaves a word when no diagonal survives -- ~0.08 POPCs per cell on "
+                          "unrelated hashes, identical runs (tests/test_match_gpu.py)",
+        "default_kernel_xu_pipe_pct": ncu_metric("profiles/r02_ncu_k3_final.txt", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
         "default_kernel_ms": match_ms_max,
         "default_kernel_algorithmic_Tcell_per_s": cells / world / (match_ms_max * 1e-3) / 1e12,
     }

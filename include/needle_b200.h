@@ -107,7 +107,11 @@ enum {
      * pipelines that go on to exchange and match on the same stream (the multi-GPU job) and
      * synchronise once at the end; host PCM passed to nb200_fingerprint_host_into must then stay
      * untouched until that synchronisation. */
-    NB200_OPT_DEFER_WAIT = 5
+    NB200_OPT_DEFER_WAIT = 5,
+    /* NB200_OPT_MATCH_BAND_GROUP (0 = automatic, 1..16): how many consecutive 256-diagonal bands of a
+     * row chunk the fast match kernel's warps claim as one unit of work.  Results never depend on it;
+     * tests force it to cover the multi-band path on small seasons. */
+    NB200_OPT_MATCH_BAND_GROUP = 6
 };
 int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value);
 

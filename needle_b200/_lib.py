@@ -30,6 +30,7 @@ OPT_K1_VARIANT = 2
 OPT_MATCH_DENSE = 3
 OPT_HOST_VOTE = 4
 OPT_DEFER_WAIT = 5
+OPT_MATCH_BAND_GROUP = 6
 
 
 class Nb200Error(RuntimeError):

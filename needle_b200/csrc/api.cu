@@ -206,6 +206,10 @@ int nb200_ctx_set_option(nb200_ctx *ctx, int option, int64_t value) {
     case NB200_OPT_DEFER_WAIT:
         ctx->defer_wait = value != 0;
         return NB200_OK;
+    case NB200_OPT_MATCH_BAND_GROUP:
+        if (value < 0 || value > 16) return NB200_ERR_INVALID_ARGUMENT;
+        ctx->match_band_group = (uint32_t)value;
+        return NB200_OK;
     case NB200_OPT_HOST_VOTE:
         ctx->host_vote = value != 0;
         return NB200_OK;

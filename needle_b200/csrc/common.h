@@ -184,6 +184,7 @@ struct nb200_ctx {
     bool ev_valid[5] = {false, false, false, false, false};
     uint64_t n_launches = 0;
     double host_ms[NB200_HOST_PHASES] = {};   // wall time spent in each host phase since the last reset
+    uint32_t match_band_group = 0;      // NB200_OPT_MATCH_BAND_GROUP (0: chosen from the tile count)
     bool match_dense = false;           // fast match kernel evaluates every cell instead of 4 sampled rows per word
     bool force_general_match = false;   // tests: run the general kernel where the fast one would be chosen
     std::shared_ptr<nb200::DevPool> pool = std::make_shared<nb200::DevPool>();

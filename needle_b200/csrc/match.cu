@@ -628,133 +628,133 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, SAMPLED ? 5 : 4) match_fast_
         int pf_score = 3;   // two words in a row must survive the first look before it is switched off
         const uint32_t *dl0 = dst_l + (248 - MATCH_C * lane);
         for (int step2 = 0; step2 < n_steps; step2 += 2) {
-          // words are taken two at a time: two independent chains through the first look
-          uint32_t todo = step2 + 1 < n_steps ? 3u : 1u;
-          if (SAMPLED && pf_score > 0) {
-              // First look, 2 POPCs for 3 cells of a diagonal (rows 0, 12, 24 of the word): if all three
-              // match, their distances add up to at most 3 T.  The three XOR words go through one
-              // carry-save adder -- ones = x0^x1^x2, twos = maj(x0,x1,x2), 4 LOP3 on the ALU pipe per diagonal --
-              // and sum = popc(ones) + 2 popc(twos).  Unrelated hashes (sum ~ 48 +- 4.9 against 3 T = 30)
-              // leave here at half the POPCs and 6 of the 10 window loads of the first 4-row stage.
-              // Exact: a word that fails cannot be full.  pf_score turns the look off while it is not
-              // paying (stationary audio, silence) and probes again at every tile.  (The second word of
-              // an odd tail is computed on whatever the buffers hold and ignored.)
-              const int lo0 = first_look(dl0 + 32 * step2, src_t + 32 * step2);
-              const int lo1 = first_look(dl0 + 32 * step2 + 32, src_t + 32 * step2 + 32);
-              // (handing the few surviving diagonals straight to coop_verify instead of the staged test was
-              // measured slower: 4.82 -> 5.51 ms on configs[3] -- a serial chain per survivor, 127 registers)
-              uint32_t surv = (__ballot_sync(0xffffffffu, lo0 <= 3 * T) ? 1u : 0u) |
-                              (__ballot_sync(0xffffffffu, lo1 <= 3 * T) ? 2u : 0u);
-              surv &= todo;
-              pf_score = min(pf_score + __popc(todo ^ surv) - 2 * __popc(surv), 8);
-              todo = surv;
-          }
+            // words are taken two at a time: two independent chains through the first look
+            uint32_t todo = step2 + 1 < n_steps ? 3u : 1u;
+            if (SAMPLED && pf_score > 0) {
+                // First look, 2 POPCs for 3 cells of a diagonal (rows 0, 12, 24 of the word): if all three
+                // match, their distances add up to at most 3 T.  The three XOR words go through one
+                // carry-save adder -- ones = x0^x1^x2, twos = maj(x0,x1,x2), 4 LOP3 on the ALU pipe per diagonal --
+                // and sum = popc(ones) + 2 popc(twos).  Unrelated hashes (sum ~ 48 +- 4.9 against 3 T = 30)
+                // leave here at half the POPCs and 6 of the 10 window loads of the first 4-row stage.
+                // Exact: a word that fails cannot be full.  pf_score turns the look off while it is not
+                // paying (stationary audio, silence) and probes again at every tile.  (The second word of
+                // an odd tail is computed on whatever the buffers hold and ignored.)
+                const int lo0 = first_look(dl0 + 32 * step2, src_t + 32 * step2);
+                const int lo1 = first_look(dl0 + 32 * step2 + 32, src_t + 32 * step2 + 32);
+                // (handing the few surviving diagonals straight to coop_verify instead of the staged test was
+                // measured slower: 4.82 -> 5.51 ms on configs[3] -- a serial chain per survivor, 127 registers)
+                uint32_t surv = (__ballot_sync(0xffffffffu, lo0 <= 3 * T) ? 1u : 0u) |
+                                (__ballot_sync(0xffffffffu, lo1 <= 3 * T) ? 2u : 0u);
+                surv &= todo;
+                pf_score = min(pf_score + __popc(todo ^ surv) - 2 * __popc(surv), 8);
+                todo = surv;
+            }
 #pragma unroll 1
-          for (int w = 0; w < 2; w++) {
-            if (((todo >> w) & 1u) == 0) continue;
-            const int step = step2 + w;
-            const uint4 *dptr = reinterpret_cast<const uint4 *>(dl0 + 32 * step);
-            int mx[MATCH_C];
+            for (int w = 0; w < 2; w++) {
+                if (((todo >> w) & 1u) == 0) continue;
+                const int step = step2 + w;
+                const uint4 *dptr = reinterpret_cast<const uint4 *>(dl0 + 32 * step);
+                int mx[MATCH_C];
 #pragma unroll
-            for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
-            if (SAMPLED) {
-                // Adaptive depth.  Stage s tests rows o, o+8, o+16, o+24 with o = bitrev3(s)
-                // (0,4,2,6,1,5,3,7): 4 more rows of every word.  The warp leaves as soon as no
-                // lane has a diagonal that still matches everywhere it was tested: one stage
-                // for unrelated hashes (p^4 ~ 4e-7), a few for correlated audio; a diagonal
-                // that survives all 8 stages has 32 matching cells.
-                uint32_t dw[40];
+                for (int c = 0; c < MATCH_C; c++) mx[c] = 0;
+                if (SAMPLED) {
+                    // Adaptive depth.  Stage s tests rows o, o+8, o+16, o+24 with o = bitrev3(s)
+                    // (0,4,2,6,1,5,3,7): 4 more rows of every word.  The warp leaves as soon as no
+                    // lane has a diagonal that still matches everywhere it was tested: one stage
+                    // for unrelated hashes (p^4 ~ 4e-7), a few for correlated audio; a diagonal
+                    // that survives all 8 stages has 32 matching cells.
+                    uint32_t dw[40];
 #pragma unroll
-                for (int q = 0; q < 10; q++) {
-                    const uint4 v = dptr[q];
-                    dw[4 * q + 0] = v.x;
-                    dw[4 * q + 1] = v.y;
-                    dw[4 * q + 2] = v.z;
-                    dw[4 * q + 3] = v.w;
-                }
-                bool alive = true;
+                    for (int q = 0; q < 10; q++) {
+                        const uint4 v = dptr[q];
+                        dw[4 * q + 0] = v.x;
+                        dw[4 * q + 1] = v.y;
+                        dw[4 * q + 2] = v.z;
+                        dw[4 * q + 3] = v.w;
+                    }
+                    bool alive = true;
 #pragma unroll
-                for (int stage = 0; stage < 8; stage++) {
-                    if (alive) {
-                        const int o = ((stage & 1) << 2) | (stage & 2) | ((stage & 4) >> 2);
-                        uint32_t sr[4];
+                    for (int stage = 0; stage < 8; stage++) {
+                        if (alive) {
+                            const int o = ((stage & 1) << 2) | (stage & 2) | ((stage & 4) >> 2);
+                            uint32_t sr[4];
 #pragma unroll
-                        for (int r = 0; r < 4; r++) sr[r] = src_t[32 * step + o + 8 * r];
+                            for (int r = 0; r < 4; r++) sr[r] = src_t[32 * step + o + 8 * r];
 #pragma unroll
-                        for (int r = 0; r < 4; r += 2) {
+                            for (int r = 0; r < 4; r += 2) {
+#pragma unroll
+                                for (int c = 0; c < MATCH_C; c++) {
+                                    const int p0 = __popc(sr[r] ^ dw[o + 8 * r + (MATCH_C - 1) - c]);
+                                    const int p1 = __popc(sr[r + 1] ^ dw[o + 8 * (r + 1) + (MATCH_C - 1) - c]);
+                                    mx[c] = max(mx[c], max(p0, p1));
+                                }
+                            }
+                            if (stage < 7) {
+                                int b2 = mx[0];
+#pragma unroll
+                                for (int c = 1; c < MATCH_C; c++) b2 = min(b2, mx[c]);
+                                const uint32_t lanes_alive = __ballot_sync(0xffffffffu, b2 <= T);
+                                alive = lanes_alive != 0;
+                                if (stage < 3 && alive && __popc(lanes_alive) <= COOP_MAX_LANES) {
+                                    uint32_t mine = 0;
+#pragma unroll
+                                    for (int c = 0; c < MATCH_C; c++) mine |= (mx[c] <= T ? 1u : 0u) << c;
+                                    coop_verify(ectx, p, src_t, dst_t, step, r0 + 32 * step, ub, Mp, M, n, lanes_alive, mine, lane);
+                                    alive = false;   // this word is done
+                                }
+                            }
+                        }
+                    }
+                    if (!alive) continue;   // warp-uniform: nothing survived
+                } else {
+                    const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
+                    uint32_t dw[40];
+#pragma unroll
+                    for (int q = 0; q < 10; q++) {
+                        const uint4 v = dptr[q];
+                        dw[4 * q + 0] = v.x;
+                        dw[4 * q + 1] = v.y;
+                        dw[4 * q + 2] = v.z;
+                        dw[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint4 sv = sptr[q];
+                        const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk += 2) {
+                            const int k = 4 * q + kk;
 #pragma unroll
                             for (int c = 0; c < MATCH_C; c++) {
-                                const int p0 = __popc(sr[r] ^ dw[o + 8 * r + (MATCH_C - 1) - c]);
-                                const int p1 = __popc(sr[r + 1] ^ dw[o + 8 * (r + 1) + (MATCH_C - 1) - c]);
-                                mx[c] = max(mx[c], max(p0, p1));
-                            }
-                        }
-                        if (stage < 7) {
-                            int b2 = mx[0];
-#pragma unroll
-                            for (int c = 1; c < MATCH_C; c++) b2 = min(b2, mx[c]);
-                            const uint32_t lanes_alive = __ballot_sync(0xffffffffu, b2 <= T);
-                            alive = lanes_alive != 0;
-                            if (stage < 3 && alive && __popc(lanes_alive) <= COOP_MAX_LANES) {
-                                uint32_t mine = 0;
-#pragma unroll
-                                for (int c = 0; c < MATCH_C; c++) mine |= (mx[c] <= T ? 1u : 0u) << c;
-                                coop_verify(ectx, p, src_t, dst_t, step, r0 + 32 * step, ub, Mp, M, n, lanes_alive, mine, lane);
-                                alive = false;   // this word is done
+                                // cell (row k, diagonal c of this lane): window element k + 7 - c
+                                const int p0 = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]);
+                                const int p1 = __popc(s4[kk + 1] ^ dw[k + 1 + (MATCH_C - 1) - c]);
+                                mx[c] = max(mx[c], max(p0, p1));     // one 3-input max per two cells
                             }
                         }
                     }
                 }
-                if (!alive) continue;   // warp-uniform: nothing survived
-            } else {
-                const uint4 *sptr = reinterpret_cast<const uint4 *>(src_t + 32 * step);
-                uint32_t dw[40];
+                int best = mx[0];
 #pragma unroll
-                for (int q = 0; q < 10; q++) {
-                    const uint4 v = dptr[q];
-                    dw[4 * q + 0] = v.x;
-                    dw[4 * q + 1] = v.y;
-                    dw[4 * q + 2] = v.z;
-                    dw[4 * q + 3] = v.w;
-                }
+                for (int c = 1; c < MATCH_C; c++) best = min(best, mx[c]);
+                // ---- rare: some diagonal of some lane has 32 matching cells in a row
+                uint32_t pending = __ballot_sync(0xffffffffu, best <= T);
+                if (pending == 0) continue;
+                uint32_t full = 0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const uint4 sv = sptr[q];
-                    const uint32_t s4[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-                    for (int kk = 0; kk < 4; kk += 2) {
-                        const int k = 4 * q + kk;
-#pragma unroll
-                        for (int c = 0; c < MATCH_C; c++) {
-                            // cell (row k, diagonal c of this lane): window element k + 7 - c
-                            const int p0 = __popc(s4[kk] ^ dw[k + (MATCH_C - 1) - c]);
-                            const int p1 = __popc(s4[kk + 1] ^ dw[k + 1 + (MATCH_C - 1) - c]);
-                            mx[c] = max(mx[c], max(p0, p1));     // one 3-input max per two cells
-                        }
+                for (int c = 0; c < MATCH_C; c++) full |= (mx[c] <= T ? 1u : 0u) << c;
+                const int i0 = r0 + 32 * step;
+                while (pending) {
+                    const int src_lane = __ffs((int)pending) - 1;
+                    pending &= pending - 1;
+                    uint32_t f = __shfl_sync(0xffffffffu, full, src_lane);
+                    while (f) {
+                        const int c = __ffs((int)f) - 1;
+                        f &= f - 1;
+                        full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, Mp, M, n, lane);
                     }
                 }
             }
-            int best = mx[0];
-#pragma unroll
-            for (int c = 1; c < MATCH_C; c++) best = min(best, mx[c]);
-            // ---- rare: some diagonal of some lane has 32 matching cells in a row
-            uint32_t pending = __ballot_sync(0xffffffffu, best <= T);
-            if (pending == 0) continue;
-            uint32_t full = 0;
-#pragma unroll
-            for (int c = 0; c < MATCH_C; c++) full |= (mx[c] <= T ? 1u : 0u) << c;
-            const int i0 = r0 + 32 * step;
-            while (pending) {
-                const int src_lane = __ffs((int)pending) - 1;
-                pending &= pending - 1;
-                uint32_t f = __shfl_sync(0xffffffffu, full, src_lane);
-                while (f) {
-                    const int c = __ffs((int)f) - 1;
-                    f &= f - 1;
-                    full_word(ectx, p, i0, ub + src_lane * MATCH_C + c, Mp, M, n, lane);
-                }
-            }
-          }
         }
         __syncwarp();   // every lane is done with this buffer: the tile after next may land in it
         if (same_unit) {
@@ -938,7 +938,8 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     {
         const uint64_t scalars[8] = {hs->n_videos, n_pairs, pair_base, params->hash_match_threshold,
                                      params->min_opening_ns, params->min_ending_ns,
-                                     (uint64_t)endings | ((uint64_t)want_fast << 1), default_flat.empty() ? 1u : 2u};
+                                     (uint64_t)endings | ((uint64_t)want_fast << 1) | ((uint64_t)ctx->match_band_group << 8),
+                                     default_flat.empty() ? 1u : 2u};
         mix(scalars, sizeof(scalars));
         mix(hs->dev_offset.data(), hs->dev_offset.size() * sizeof(uint32_t));
         mix(hs->seg_len.data(), hs->seg_len.size() * sizeof(uint32_t));
@@ -1007,10 +1008,12 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
             }
         }
         // fast kernel: bands are claimed in groups (units) so that the per-claim work is amortised, but
-        // never so large that a persistent warp gets fewer than ~12 units
+        // never so large that a persistent warp gets fewer than ~32 units (the last unit of the slowest
+        // warp is the kernel's tail: 8 % of a rank's 0.6 ms at N = 8 with 15 units per warp)
         {
             const uint64_t warps = (uint64_t)ctx->sm_count * 5 * MATCH_WARPS;
-            const uint32_t G = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, tiles_f / (warps * 12)));
+            const uint32_t G = ctx->match_band_group ? ctx->match_band_group
+                                                     : (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, tiles_f / (warps * 32)));
             uint64_t units = 0;
             for (MatchProblem &pr : prob_f) {
                 const uint64_t chunks = (pr.n + MATCH_R - 1) / MATCH_R;

@@ -67,7 +67,7 @@ class Context:
         check(lib().nb200_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None),
               "nb200_ctx_set_stream")
 
-    OPT_FORCE_GENERAL_MATCH, OPT_K1_VARIANT, OPT_MATCH_DENSE, OPT_HOST_VOTE, OPT_DEFER_WAIT = 1, 2, 3, 4, 5
+    OPT_FORCE_GENERAL_MATCH, OPT_K1_VARIANT, OPT_MATCH_DENSE, OPT_HOST_VOTE, OPT_DEFER_WAIT, OPT_MATCH_BAND_GROUP = 1, 2, 3, 4, 5, 6
 
     def set_option(self, option: int, value: int):
         check(lib().nb200_ctx_set_option(self._h, option, value), "nb200_ctx_set_option")

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from needle_b200 import engine, synth
-from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, OPT_MATCH_DENSE, OPT_HOST_VOTE, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
+from needle_b200._lib import OPT_FORCE_GENERAL_MATCH, OPT_MATCH_DENSE, OPT_HOST_VOTE, OPT_MATCH_BAND_GROUP, ERR_DURATION_UNDERFLOW, ERR_NO_ENDING, ERR_COMPARATOR_MINIMUM_PATHS, Nb200Error
 from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -93,6 +93,19 @@ def test_random_short_min_durations(ctx, oracle, min_s):
     ns = int(min_s * 1e9)
     check_season(ctx, oracle, season, vote=min_s >= 0.5, threshold=13, include_endings=True, min_opening_ns=ns,
                  min_ending_ns=ns // 2)
+
+
+@pytest.mark.parametrize("group", [1, 2, 3, 16])
+def test_band_groups(ctx, oracle, group):
+    """The fast kernel's unit of work = `group` consecutive bands of a row chunk (src rows fetched once,
+    the dst window moved band by band): lists of 3-5 bands, ragged, with runs that cross band and chunk
+    borders; every group size gives the oracle's runs."""
+    season = synth.make_hash_season(5, 1100, 600, seed=30 + group, run_len=300, jitter_len=True)
+    ctx.set_option(OPT_MATCH_BAND_GROUP, group)
+    try:
+        check_season(ctx, oracle, season, include_endings=True)
+    finally:
+        ctx.set_option(OPT_MATCH_BAND_GROUP, 0)
 
 
 def test_planted_season_defaults(ctx, oracle):

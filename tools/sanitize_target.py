@@ -10,7 +10,7 @@ rng = np.random.default_rng(0)
 lens = [0, 4095, 4096, 4096 + 1365 * 19, 4096 + 1365 * 40 + 7, 60_001, 90_000, 33_333]
 segs = [rng.integers(-20000, 20000, n).astype(np.int16) for n in lens]
 ref = None
-for variant in (0, 1, 8, 10, 12, 16, 17, 18, 112):
+for variant in (0, 1, 8, 10, 12, 16, 17, 18, 19, 112):
     ctx.set_option(2, variant)
     out = ctx.fingerprint_batch(segs)
     if ref is None:
@@ -29,6 +29,20 @@ for params in (engine.match_params(include_endings=True),
                engine.match_params(include_endings=True, min_opening_ns=0, min_ending_ns=10 ** 9, threshold=12)):
     runs = ctx.match_pairs(season.hashes, season.ts_ns, season.seg_offset, params)
     ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
+# band groups of the fast kernel, page-locked input (direct copy + device-side move into the aligned layout)
+long_season = synth.make_hash_season(3, 1100, 600, seed=5, run_len=300, jitter_len=True)
+pin_h = engine.PinnedArray.empty(long_season.hashes.size, np.uint32)
+pin_t = engine.PinnedArray.empty(long_season.ts_ns.size, np.uint64)
+pin_h.array[:] = long_season.hashes
+pin_t.array[:] = long_season.ts_ns
+want = ctx.match_pairs(long_season.hashes, long_season.ts_ns, long_season.seg_offset, engine.match_params(include_endings=True))
+for group in (2, 16):
+    ctx.set_option(6, group)
+    got = ctx.match_pairs(pin_h.array, pin_t.array, long_season.seg_offset, engine.match_params(include_endings=True))
+    assert np.array_equal(got, want)
+ctx.set_option(6, 0)
+pin_h.free()
+pin_t.free()
 # device vote vs host vote, the PCM-resident fused call, run blocks (export -> vote_blocks)
 hs = engine.HashSet.upload(ctx, season.hashes, season.ts_ns, season.seg_offset)
 for params in (engine.match_params(include_endings=True),

@@ -7,7 +7,7 @@ OUT=${1:-profiles/r02_sass_k1_k3.txt}
 {
 echo "# cuobjdump -sass of needle_b200/_obj/*.o (sm_100a), built by needle_b200/build.py"
 echo "# PTX -> SASS: cp.async.bulk -> UBLKCP, mbarrier expect_tx/try_wait -> SYNCS, tcgen05.ld/st -> LDTM/STTM, tcgen05.alloc/dealloc -> UTCATOMSWS"
-for spec in "fingerprint.o:_ZN5nb20023fp_fft_chroma_tm_kernelILi16ELi2EEEvNS_6K1ArgsE:K1 fp_fft_chroma_tm_kernel<16,2> (default)" \
+for spec in "fingerprint.o:_ZN5nb20023fp_fft_chroma_tm_kernelILi16ELi4EEEvNS_6K1ArgsE:K1 fp_fft_chroma_tm_kernel<16,4> (default)" \
             "match.o:_ZN5nb20017match_fast_kernelILb1EEEvNS_9MatchArgsE:K3 match_fast_kernel<adaptive> (default)" \
             "match.o:_ZN5nb20017match_fast_kernelILb0EEEvNS_9MatchArgsE:K3 match_fast_kernel<dense>" \
             "match.o:_ZN5nb20012match_kernelENS_9MatchArgsE:K3 match_kernel (general)"; do
