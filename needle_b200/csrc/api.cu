@@ -449,6 +449,91 @@ static int hashset_upload_impl(nb200_ctx *ctx, const uint32_t *hashes, const uin
     return NB200_OK;
 }
 
+}   // extern "C"
+
+namespace nb200 {
+
+int hashset_upload_slice(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
+                         uint32_t n_videos, int rank, int world, SliceUpload *su, nb200_hashset **out) {
+    if (!ctx || !seg_offset || !su || !out || !hashes || !ts_ns) return NB200_ERR_NULL_ARGUMENT;
+    *out = nullptr;
+    if (seg_offset[0] != 0 || world < 1 || rank < 0 || rank >= world) return NB200_ERR_INVALID_ARGUMENT;
+    NB_CUDA(cudaSetDevice(ctx->device));
+    nb200_hashset *hs = new (std::nothrow) nb200_hashset();
+    if (!hs) return NB200_ERR_TOO_LARGE;
+    int st = layout_hashset(hs, seg_offset, n_videos);
+    if (st == NB200_OK && hs->total == 0) st = NB200_ERR_INVALID_ARGUMENT;   // callers take the plain upload for an empty season
+    if (st != NB200_OK) {
+        delete hs;
+        return st;
+    }
+    const uint32_t nseg = 2 * n_videos;
+    const size_t p_t = (size_t)hs->total * sizeof(uint64_t), image = p_t + (size_t)hs->total * sizeof(uint32_t);
+    const size_t slice = ((image + (size_t)world - 1) / (size_t)world + 15) & ~size_t(15);
+    const size_t b_off = (size_t)(nseg + 1) * sizeof(uint64_t), b_dev = (size_t)nseg * sizeof(uint32_t);
+    if (ctx->d_upload.reserve(slice * (size_t)world + b_off + b_dev) != NB200_OK ||
+        ctx->h_upload.reserve(slice + b_off + b_dev) != NB200_OK ||
+        hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
+        hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK) {
+        delete hs;
+        return NB200_ERR_CUDA;
+    }
+    cudaStream_t s = ctx->stream;
+    char *scratch = ctx->d_upload.as<char>();
+    char *stage = ctx->h_upload.as<char>();
+    cudaError_t e = cudaEventSynchronize(ctx->ev_chunk[12]);
+    // this rank's bytes [lo, hi) of the image: a piece of the timestamps and/or a piece of the hashes
+    const size_t lo = std::min(image, slice * (size_t)rank), hi = std::min(image, lo + slice);
+    const size_t t_lo = std::min(lo, p_t), t_hi = std::min(hi, p_t), h_lo = std::max(lo, p_t) - p_t, h_hi = std::max(hi, p_t) - p_t;
+    const bool direct = is_pinned_host(hashes) && is_pinned_host(ts_ns);
+    const char *from_t = reinterpret_cast<const char *>(ts_ns) + t_lo, *from_h = reinterpret_cast<const char *>(hashes) + h_lo;
+    if (e == cudaSuccess && !direct) {   // ordinary memory: through the pinned staging area
+        if (t_hi > t_lo) memcpy(stage, from_t, t_hi - t_lo);
+        if (h_hi > h_lo) memcpy(stage + (t_hi - t_lo), from_h, h_hi - h_lo);
+        from_t = stage;
+        from_h = stage + (t_hi - t_lo);
+    }
+    if (e == cudaSuccess && t_hi > t_lo) e = cudaMemcpyAsync(scratch + t_lo, from_t, t_hi - t_lo, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && h_hi > h_lo) e = cudaMemcpyAsync(scratch + p_t + h_lo, from_h, h_hi - h_lo, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        memcpy(stage + slice, hs->seg_offset.data(), b_off);
+        memcpy(stage + slice + b_off, hs->dev_offset.data(), b_dev);
+        e = cudaMemcpyAsync(scratch + slice * (size_t)world, stage + slice, b_off + b_dev, cudaMemcpyHostToDevice, s);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[12], s);
+    if (e != cudaSuccess) {
+        cudaStreamSynchronize(s);
+        set_last_error("hashset_upload_slice", e);
+        delete hs;
+        return NB200_ERR_CUDA;
+    }
+    su->d_pack = scratch;
+    su->slice_bytes = slice;
+    *out = hs;
+    return NB200_OK;
+}
+
+int hashset_upload_finish(nb200_ctx *ctx, nb200_hashset *hs, const SliceUpload &su, int world) {
+    NB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t nseg = 2 * hs->n_videos;
+    const size_t p_t = (size_t)hs->total * sizeof(uint64_t);
+    const char *tables = su.d_pack + su.slice_bytes * (size_t)world;
+    NB_CUDA(cudaMemsetAsync(hs->d_hashes.p, 0, (size_t)hs->dev_total * sizeof(uint32_t), s));
+    NB_CUDA(cudaMemsetAsync(hs->d_ts.p, 0, (size_t)hs->dev_total * sizeof(uint64_t), s));
+    repack_kernel<<<(unsigned)((hs->total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<const uint32_t *>(su.d_pack + p_t), reinterpret_cast<const uint64_t *>(su.d_pack),
+        hs->d_hashes.as<uint32_t>(), hs->d_ts.as<uint64_t>(), reinterpret_cast<const uint64_t *>(tables),
+        reinterpret_cast<const uint32_t *>(tables + (size_t)(nseg + 1) * sizeof(uint64_t)), nseg, hs->total);
+    NB_CUDA(cudaGetLastError());
+    ctx->n_launches++;
+    return NB200_OK;
+}
+
+}   // namespace nb200
+
+extern "C" {
+
 int nb200_hashset_upload(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
                          const uint64_t *seg_offset, uint32_t n_videos, nb200_hashset **out) {
     return hashset_upload_impl(ctx, hashes, ts_ns, seg_offset, n_videos, true, out);

@@ -323,6 +323,19 @@ int vote_impl(const uint64_t *hash_duration_ns, uint32_t n_videos, const uint32_
               uint64_t n_pairs, const nb200_match_params *params, const nb200_run *runs,
               uint64_t n_runs, const uint8_t *video_mask, nb200_search_result *results);
 
+// api.cu ------------------------------------------------------------------
+// A season uploaded 1/world per rank (multi.cu's search job): every rank copies ONE slice of the packed
+// byte image [ts | hashes] of the caller's arrays into its scratch, the ranks all-gather the scratch in
+// place over NVLink (the caller: d_pack + rank * slice_bytes -> d_pack, slice_bytes each), then every rank
+// moves the image into its own aligned season.  Host staging and PCIe traffic per rank fall by `world`.
+struct SliceUpload {
+    char *d_pack = nullptr;
+    size_t slice_bytes = 0;
+};
+int hashset_upload_slice(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns, const uint64_t *seg_offset,
+                         uint32_t n_videos, int rank, int world, SliceUpload *su, nb200_hashset **out);
+int hashset_upload_finish(nb200_ctx *ctx, nb200_hashset *hs, const SliceUpload &su, int world);
+
 // fingerprint.cu -----------------------------------------------------------
 int fingerprint_run_impl(nb200_ctx *ctx, const nb200_pcmset *ps, uint32_t stride, uint64_t delay_ns,
                          uint64_t item_ns, const uint64_t *seek_to_ns, nb200_hashset **out);

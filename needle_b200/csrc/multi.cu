@@ -535,7 +535,7 @@ static int mjob_common(nb200_mjob *j, nb200_comm *const *comms, int n_local, con
 static int mjob_alloc_blocks(nb200_mjob *j) {
     for (auto &R : j->ranks) {
         NB_CUDA(cudaSetDevice(R.comm->ctx->device));
-        NB_TRY(R.d_block.alloc(64 * (1 + j->run_cap)));
+        NB_TRY(R.d_block.alloc(64 * (1 + j->run_cap), R.comm->ctx->pool));   // a job per search must not pay cudaMalloc + cudaFree
     }
     return NB200_OK;
 }
@@ -774,9 +774,43 @@ int nb200_mjob_search_create(nb200_comm *const *comms, int n_local, const uint32
         j->run_cap = pick_run_cap(j);
         st = mjob_alloc_blocks(j);
     }
-    // every rank holds the whole season: it is KB..MB (BASELINE configs[3]: 10 MB)
-    for (size_t k = 0; st == NB200_OK && k < j->ranks.size(); k++)
-        st = nb200_hashset_upload(j->ranks[k].comm->ctx, hashes, ts_ns, seg_offset, n_videos, &j->ranks[k].season);
+    // Every rank holds the whole season (KB..MB; BASELINE configs[3]: 10 MB), but no rank copies all of it
+    // from the host: each takes 1/world of the packed image over PCIe and the ranks all-gather it in place
+    // over NVLink -- host staging and H2D traffic per rank fall by `world`.
+    if (st == NB200_OK && j->world > 1 && seg_offset[2 * (size_t)n_videos] > 0) {
+        st = need_nccl();
+        std::vector<SliceUpload> su(j->ranks.size());
+        for (size_t k = 0; st == NB200_OK && k < j->ranks.size(); k++) {
+            nb200_comm *c = j->ranks[k].comm;
+            st = hashset_upload_slice(c->ctx, hashes, ts_ns, seg_offset, n_videos, c->rank, j->world, &su[k], &j->ranks[k].season);
+        }
+        if (st == NB200_OK) {
+            ncclResult_t r = nccl_api().GroupStart();
+            for (size_t k = 0; r == ncclSuccess && k < j->ranks.size(); k++) {
+                nb200_comm *c = j->ranks[k].comm;
+                r = nccl_api().AllGather(su[k].d_pack + su[k].slice_bytes * (size_t)c->rank, su[k].d_pack, su[k].slice_bytes,
+                                         ncclUint8, c->nccl, c->ctx->stream);
+            }
+            const ncclResult_t r2 = nccl_api().GroupEnd();
+            if (r != ncclSuccess || r2 != ncclSuccess) {
+                set_last_error_msg(std::string("ncclAllGather(season image): ") + nccl_api().GetErrorString(r != ncclSuccess ? r : r2));
+                st = NB200_ERR_NCCL;
+            }
+        }
+        for (size_t k = 0; st == NB200_OK && k < j->ranks.size(); k++)
+            st = hashset_upload_finish(j->ranks[k].comm->ctx, j->ranks[k].season, su[k], j->world);
+        // the caller's arrays and the staging areas are free again when this returns
+        for (size_t k = 0; st == NB200_OK && k < j->ranks.size(); k++) {
+            if (cudaSetDevice(j->ranks[k].comm->ctx->device) != cudaSuccess ||
+                cudaStreamSynchronize(j->ranks[k].comm->ctx->stream) != cudaSuccess) {
+                set_last_error("nb200_mjob_search_create", cudaGetLastError());
+                st = NB200_ERR_CUDA;
+            }
+        }
+    } else {
+        for (size_t k = 0; st == NB200_OK && k < j->ranks.size(); k++)
+            st = nb200_hashset_upload(j->ranks[k].comm->ctx, hashes, ts_ns, seg_offset, n_videos, &j->ranks[k].season);
+    }
     if (st != NB200_OK) {
         nb200_mjob_free(j);
         return st;
@@ -850,8 +884,9 @@ int nb200_mjob_season_create(nb200_comm *const *comms, int n_local, const uint64
             R.my_n_mono.push_back(j->n_mono[s]);
         }
         const size_t total = (size_t)j->cap * world;
-        if (R.d_hash_send.alloc(j->cap * 4) != NB200_OK || R.d_ts_send.alloc(j->cap * 8) != NB200_OK ||
-            R.d_hash_recv.alloc(total * 4) != NB200_OK || R.d_ts_recv.alloc(total * 8) != NB200_OK)
+        const auto &pool = R.comm->ctx->pool;
+        if (R.d_hash_send.alloc(j->cap * 4, pool) != NB200_OK || R.d_ts_send.alloc(j->cap * 8, pool) != NB200_OK ||
+            R.d_hash_recv.alloc(total * 4, pool) != NB200_OK || R.d_ts_recv.alloc(total * 8, pool) != NB200_OK)
             return fail(NB200_ERR_CUDA);
         if (cudaMemsetAsync(R.d_hash_send.p, 0, j->cap * 4, ctx->stream) != cudaSuccess ||
             cudaMemsetAsync(R.d_hash_recv.p, 0, total * 4, ctx->stream) != cudaSuccess)

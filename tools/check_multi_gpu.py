@@ -79,6 +79,18 @@ def run_jobs(comms, n_videos, segs, seeks, params, pairs, season, params0):
     job = engine.MultiJob.search(comms, season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
     out["search"] = job.run()
     job.free()
+    # the same season from page-locked arrays (each rank copies its slice of the image directly)
+    pin_h = engine.PinnedArray.empty(season.hashes.size, np.uint32)
+    pin_t = engine.PinnedArray.empty(season.ts_ns.size, np.uint64)
+    pin_h.array[:] = season.hashes
+    pin_t.array[:] = season.ts_ns
+    job = engine.MultiJob.search(comms, pin_h.array, pin_t.array, season.seg_offset, season.hash_duration_ns, params)
+    pin_h.array[:] = 0    # released by the create call
+    pin_t.array[:] = 0
+    out["search_pinned"] = job.run()
+    job.free()
+    pin_h.free()
+    pin_t.free()
     # thousands of runs per rank: the first attempt's blocks (4096 records) overflow
     job = engine.MultiJob.search(comms, season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params0)
     out["search_overflow"] = job.run()
@@ -92,6 +104,7 @@ def compare(out, want, sub, want_search, want_dense, want_few):
     assert out["default_host"] == want
     assert out["explicit_resident"] == sub and out["explicit_host"] == sub
     assert out["search"] == want_search
+    assert out["search_pinned"] == want_search
     assert out["few_videos"] == want_few
     assert out["search_overflow"] == want_dense and out["search_overflow_again"] == want_dense
     assert sum(r[1] for r in want_search) >= 8
