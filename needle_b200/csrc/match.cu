@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, SAMPLED ? 5 : 4) match_fast_
     __shared__ __align__(128) uint32_t s_dst[MATCH_WARPS][2][FAST_DST_TILE];
     // A second copy of the dst window, 16 bytes further into its 128-byte line.  A lane's 16-byte loads
     // are 32 bytes from its neighbour's, so the 8 lanes of one wavefront would cover only 4 of the 8
-    // 16-byte bank groups twice (r02_ncu_k3_final.txt: 11.6 M conflict wavefronts, the LSU data pipe at
+    // 16-byte bank groups twice (r02_ncu_k3_trail.txt, step 0: 11.6 M conflict wavefronts, the LSU data pipe at
     // 73 %); lanes with bit 2 set read this copy and land on the other 4 groups.
     __shared__ __align__(128) uint32_t s_dst_b[MATCH_WARPS][2][FAST_DST_TILE + 32];
     __shared__ __align__(8) uint64_t s_bar[MATCH_WARPS][2];
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32, SAMPLED ? 5 : 4) match_fast_
     // What a warp claims from the global cursor is a UNIT: one row chunk x up to a.band_group consecutive
     // bands (tiles) of one problem.  The atomic, the LUT walk, the descriptor loads and the divisions --
     // a chain of dependent L2 round trips, a third of the kernel's stall samples when paid per tile
-    // (profiles/r02_ncu_k3_v2.txt) -- are paid once per unit; the src rows are fetched once per unit;
+    // (profiles/r02_ncu_k3_trail.txt, step 1) -- are paid once per unit; the src rows are fetched once per unit;
     // from band to band only the dst window moves, by 256 columns.
     struct Unit {
         uint32_t p;
