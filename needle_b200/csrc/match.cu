@@ -905,12 +905,10 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
     clamped.hash_match_threshold = std::min<uint32_t>(params->hash_match_threshold, 32u);
     params = &clamped;
     NB_CUDA(cudaSetDevice(ctx->device));
+    // NULL = every (i < j) in the reference's order; the list itself is only built when the plan is
+    const bool all_pairs = pairs == nullptr;
     std::vector<uint32_t> default_flat;
-    if (!pairs) {
-        default_pairs(hs->n_videos, default_flat);
-        pairs = reinterpret_cast<const uint32_t(*)[2]>(default_flat.data());
-        n_pairs = default_flat.size() / 2;
-    }
+    if (all_pairs) n_pairs = (uint64_t)hs->n_videos * (hs->n_videos ? hs->n_videos - 1 : 0) / 2;
     if (2 * (n_pairs + (uint64_t)pair_base) >= 0xffffffffull) return NB200_ERR_TOO_LARGE;
     const bool endings = params->include_endings != 0;
     const bool want_fast = !ctx->force_general_match;
@@ -939,17 +937,21 @@ int match_enqueue(nb200_ctx *ctx, const nb200_hashset *hs_c, const uint32_t (*pa
         const uint64_t scalars[8] = {hs->n_videos, n_pairs, pair_base, params->hash_match_threshold,
                                      params->min_opening_ns, params->min_ending_ns,
                                      (uint64_t)endings | ((uint64_t)want_fast << 1) | ((uint64_t)ctx->match_band_group << 8),
-                                     default_flat.empty() ? 1u : 2u};
+                                     all_pairs ? 2u : 1u};
         mix(scalars, sizeof(scalars));
         mix(hs->dev_offset.data(), hs->dev_offset.size() * sizeof(uint32_t));
         mix(hs->seg_len.data(), hs->seg_len.size() * sizeof(uint32_t));
-        if (default_flat.empty()) mix(pairs, (size_t)n_pairs * 8);
+        if (!all_pairs) mix(pairs, (size_t)n_pairs * 8);
     }
     MatchPlanCache &pc = ctx->match_plan;
     const bool hit = pc.valid && pc.key == key;
     const uint32_t nseg = 2 * hs->n_videos;
     if (!hit) {
         pc.valid = false;
+        if (all_pairs) {
+            default_pairs(hs->n_videos, default_flat);
+            pairs = reinterpret_cast<const uint32_t(*)[2]>(default_flat.data());
+        }
         // every list as a dst of the fast kernel: period and place of its repeated live columns
         std::vector<Dst2Seg> d2(nseg);
         uint64_t d2_total = 0;
