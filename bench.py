@@ -11,8 +11,10 @@ C ABI of include/needle_b200.h (multi-GPU: nb200_comm_* / nb200_mjob_*):
   search       BASELINE configs[3]: search-only from precomputed hashes, 200 episodes x 24 min,
                19,900 pairs, openings + endings; the pair list is sharded over the ranks by table
                cells, every rank's runs are pushed to rank 0 over NVLink, rank 0 votes.
-               -> `value` (pairs/s, hashes resident in HBM) and `e2e` (host hash arrays in,
-               per-video results out, every step).
+               -> `value` (pairs/s, hashes resident in HBM) and `e2e` (page-locked host hash +
+               timestamp arrays in, per-video results out, every step: nb200_search; at N > 1 a job
+               created -- every rank copies 1/N of the season, one all-gather over NVLink -- run and
+               freed per step); `e2e.pageable_input` = the same from ordinary memory.
   fingerprint  BASELINE configs[4]: fingerprint-only, 1000 audio-hours of 11025 Hz mono PCM
                (3,334 episodes x 24 min, opening 50 % + ending 25 % of each = 18 min), episodes
                sharded over the ranks, PCM resident in HBM -> `fingerprint.value`
