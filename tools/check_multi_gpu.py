@@ -33,6 +33,17 @@ def workload():
     return n_videos, segs, seeks
 
 
+def tiny_season():
+    h = np.arange(1, 13, dtype=np.uint32) * np.uint32(2654435761)
+    e = np.arange(1, 6, dtype=np.uint32) * np.uint32(40503)
+    ts = lambda n, seek=0: synth.hash_timestamps(2 * n, 2, seek_to_ns=seek)[:n]
+    hashes = np.concatenate([h, e, h, e])
+    ts_ns = np.concatenate([ts(12), ts(5, 10 ** 12), ts(12), ts(5, 10 ** 12)])
+    off = np.array([0, 12, 17, 29, 34], np.uint64)
+    season = synth.HashSeason(hashes, ts_ns, off, np.full(2, synth.HASH_DURATION_NS, np.uint64))
+    return season, engine.match_params(threshold=2, include_endings=True, min_opening_ns=10 ** 9, min_ending_ns=5 * 10 ** 8)
+
+
 def single_gpu_truth(device, n_videos, segs, seeks, params, pairs, season, params0):
     from oracle import oracle as orc
     with engine.Context(device) as ctx:
@@ -44,13 +55,16 @@ def single_gpu_truth(device, n_videos, segs, seeks, params, pairs, season, param
         want_search = ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params)
         want_dense = ctx.search(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params0)
         want_few = ctx.analyze_search(segs[:6], 1, seeks[:6], synth.HASH_DURATION_NS, params)
+        tiny, tiny_params = tiny_season()
+        want_tiny = ctx.search(tiny.hashes, tiny.ts_ns, tiny.seg_offset, tiny.hash_duration_ns, tiny_params)
+        assert sum(r[1] for r in want_tiny) == 2 and sum(r[2] for r in want_tiny) == 2, want_tiny
     # the oracle on the precomputed-hash season (bit-exact bar)
     s = orc.Season(season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns)
     st, ref, _ = orc.run_with_frame_hashes(s, include_endings=True)
     assert st == 0 and [tuple(int(x) for x in r) for r in ref] == [tuple(int(x) for x in r) for r in want_search], \
         "single-GPU search differs from the oracle"
     assert sum(r[1] for r in want) == n_videos, want
-    return want, sub, want_search, want_dense, want_few
+    return want, sub, want_search, want_dense, want_few, want_tiny
 
 
 def run_jobs(comms, n_videos, segs, seeks, params, pairs, season, params0):
@@ -91,6 +105,12 @@ def run_jobs(comms, n_videos, segs, seeks, params, pairs, season, params0):
     job.free()
     pin_h.free()
     pin_t.free()
+    # a season smaller than the world: 2 videos (1 pair), 12 + 5 hashes each -- most ranks get an empty slice
+    # of the image and no pair at all
+    tiny, tiny_params = tiny_season()
+    job = engine.MultiJob.search(comms, tiny.hashes, tiny.ts_ns, tiny.seg_offset, tiny.hash_duration_ns, tiny_params)
+    out["search_tiny"] = job.run()
+    job.free()
     # thousands of runs per rank: the first attempt's blocks (4096 records) overflow
     job = engine.MultiJob.search(comms, season.hashes, season.ts_ns, season.seg_offset, season.hash_duration_ns, params0)
     out["search_overflow"] = job.run()
@@ -99,12 +119,13 @@ def run_jobs(comms, n_videos, segs, seeks, params, pairs, season, params0):
     return out
 
 
-def compare(out, want, sub, want_search, want_dense, want_few):
+def compare(out, want, sub, want_search, want_dense, want_few, want_tiny):
     assert out["default_resident"] == want, (out["default_resident"], want)
     assert out["default_host"] == want
     assert out["explicit_resident"] == sub and out["explicit_host"] == sub
     assert out["search"] == want_search
     assert out["search_pinned"] == want_search
+    assert out["search_tiny"] == want_tiny
     assert out["few_videos"] == want_few
     assert out["search_overflow"] == want_dense and out["search_overflow_again"] == want_dense
     assert sum(r[1] for r in want_search) >= 8
