@@ -340,6 +340,16 @@ bool is_pinned_host(const void *p) {
 }
 }   // namespace
 
+// The staging area of the uploads may still feed the previous upload's copies: wait for them before the
+// area is written again -- or replaced by a larger one (PinnedBuf::reserve frees the old block).
+static int upload_staging_idle(nb200_ctx *ctx) {
+    if (cudaEventSynchronize(ctx->ev_chunk[12]) != cudaSuccess) {
+        set_last_error("cudaEventSynchronize(upload staging)", cudaGetLastError());
+        return NB200_ERR_CUDA;
+    }
+    return NB200_OK;
+}
+
 // `wait`: the caller's arrays may be reused as soon as this returns (the public upload).  The fused calls
 // (nb200_search, nb200_match_pairs) pass false: they wait for the whole pipeline before they return.
 static int hashset_upload_impl(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t *ts_ns,
@@ -365,19 +375,17 @@ static int hashset_upload_impl(nb200_ctx *ctx, const uint32_t *hashes, const uin
         const size_t p_t = (size_t)hs->total * sizeof(uint64_t), p_h = ((size_t)hs->total * sizeof(uint32_t) + 15) & ~size_t(15);
         const size_t b_off = (size_t)(nseg + 1) * sizeof(uint64_t), b_dev = (size_t)nseg * sizeof(uint32_t);
         cudaStream_t s = ctx->stream;
-        if (ctx->d_upload.reserve(p_t + p_h + b_off + b_dev) != NB200_OK || ctx->h_upload.reserve(b_off + b_dev) != NB200_OK ||
+        if (upload_staging_idle(ctx) != NB200_OK ||
+            ctx->d_upload.reserve(p_t + p_h + b_off + b_dev) != NB200_OK || ctx->h_upload.reserve(b_off + b_dev) != NB200_OK ||
             hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
             hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK) {
             delete hs;
             return NB200_ERR_CUDA;
         }
-        cudaError_t e = cudaEventSynchronize(ctx->ev_chunk[12]);
         char *scratch = ctx->d_upload.as<char>();
-        if (e == cudaSuccess) {
-            memcpy(ctx->h_upload.p, hs->seg_offset.data(), b_off);
-            memcpy(ctx->h_upload.as<char>() + b_off, hs->dev_offset.data(), b_dev);
-            e = cudaMemcpyAsync(scratch + p_t, hashes, (size_t)hs->total * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
-        }
+        memcpy(ctx->h_upload.p, hs->seg_offset.data(), b_off);
+        memcpy(ctx->h_upload.as<char>() + b_off, hs->dev_offset.data(), b_dev);
+        cudaError_t e = cudaMemcpyAsync(scratch + p_t, hashes, (size_t)hs->total * sizeof(uint32_t), cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(scratch, ts_ns, p_t, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaMemcpyAsync(scratch + p_t + p_h, ctx->h_upload.p, b_off + b_dev, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[12], s);
@@ -408,13 +416,8 @@ static int hashset_upload_impl(nb200_ctx *ctx, const uint32_t *hashes, const uin
     // (one core moves ~10 GB/s: 1 ms for the 10.4 MB of a 200-episode season, as long as a fifth of its search).
     const size_t b_h = (size_t)hs->dev_total * sizeof(uint32_t);
     const size_t b_t = (size_t)hs->dev_total * sizeof(uint64_t);
-    if (ctx->h_upload.reserve(b_h + b_t + 16) != NB200_OK || hs->d_hashes.alloc(b_h, ctx->pool) != NB200_OK ||
-        hs->d_ts.alloc(b_t, ctx->pool) != NB200_OK) {
-        delete hs;
-        return NB200_ERR_CUDA;
-    }
-    if (cudaEventSynchronize(ctx->ev_chunk[12]) != cudaSuccess) {
-        set_last_error("cudaEventSynchronize(upload staging)", cudaGetLastError());
+    if (upload_staging_idle(ctx) != NB200_OK || ctx->h_upload.reserve(b_h + b_t + 16) != NB200_OK ||
+        hs->d_hashes.alloc(b_h, ctx->pool) != NB200_OK || hs->d_ts.alloc(b_t, ctx->pool) != NB200_OK) {
         delete hs;
         return NB200_ERR_CUDA;
     }
@@ -471,7 +474,7 @@ int hashset_upload_slice(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t 
     const size_t p_t = (size_t)hs->total * sizeof(uint64_t), image = p_t + (size_t)hs->total * sizeof(uint32_t);
     const size_t slice = ((image + (size_t)world - 1) / (size_t)world + 15) & ~size_t(15);
     const size_t b_off = (size_t)(nseg + 1) * sizeof(uint64_t), b_dev = (size_t)nseg * sizeof(uint32_t);
-    if (ctx->d_upload.reserve(slice * (size_t)world + b_off + b_dev) != NB200_OK ||
+    if (upload_staging_idle(ctx) != NB200_OK || ctx->d_upload.reserve(slice * (size_t)world + b_off + b_dev) != NB200_OK ||
         ctx->h_upload.reserve(slice + b_off + b_dev) != NB200_OK ||
         hs->d_hashes.alloc((size_t)hs->dev_total * sizeof(uint32_t), ctx->pool) != NB200_OK ||
         hs->d_ts.alloc((size_t)hs->dev_total * sizeof(uint64_t), ctx->pool) != NB200_OK) {
@@ -481,7 +484,7 @@ int hashset_upload_slice(nb200_ctx *ctx, const uint32_t *hashes, const uint64_t 
     cudaStream_t s = ctx->stream;
     char *scratch = ctx->d_upload.as<char>();
     char *stage = ctx->h_upload.as<char>();
-    cudaError_t e = cudaEventSynchronize(ctx->ev_chunk[12]);
+    cudaError_t e = cudaSuccess;
     // this rank's bytes [lo, hi) of the image: a piece of the timestamps and/or a piece of the hashes
     const size_t lo = std::min(image, slice * (size_t)rank), hi = std::min(image, lo + slice);
     const size_t t_lo = std::min(lo, p_t), t_hi = std::min(hi, p_t), h_lo = std::max(lo, p_t) - p_t, h_hi = std::max(hi, p_t) - p_t;
