@@ -175,3 +175,30 @@ def test_threaded_oracle_equals_serial(oracle):
     a = oracle.run_with_frame_hashes(s, include_endings=True, n_threads=1, want_entries=True)
     b = oracle.run_with_frame_hashes(s, include_endings=True, n_threads=4, want_entries=True)
     assert a == b
+
+
+def _identical_pair_season():
+    """Two videos with the same 12-hash opening and 5-hash ending."""
+    h = np.arange(1, 13, dtype=np.uint32) * np.uint32(2654435761)
+    e = np.arange(1, 6, dtype=np.uint32) * np.uint32(40503)
+    ts = lambda n, seek=0: synth.hash_timestamps(2 * n, 2, seek_to_ns=seek)[:n]
+    return synth.HashSeason(np.concatenate([h, e, h, e]),
+                            np.concatenate([ts(12), ts(5, 10 ** 12), ts(12), ts(5, 10 ** 12)]),
+                            np.array([0, 12, 17, 29, 34], np.uint64), np.full(2, synth.HASH_DURATION_NS, np.uint64))
+
+
+def test_q6_threshold_zero_finds_runs_but_votes_for_nothing(oracle):
+    """comparator.rs:441 skips a candidate pair when dist >= T + T/2: with T = 0 that is every pair, the
+    candidate itself included, so every cluster is empty and find_best_match has no winner although the
+    pair tables hold runs (both videos are `present`).  Both the C oracle and the Python transcription."""
+    season = _identical_pair_season()
+    kw = H.params_kw(threshold=0, include_endings=True, min_opening_ns=S, min_ending_ns=S // 2)
+    st, got, entries = H.oracle_run(oracle, season, **kw)
+    assert st == 0
+    assert got == [(1, 0, 0, 0, 0, 0, 0), (1, 0, 0, 0, 0, 0, 0)]
+    assert len(H.entries_as_runs(entries)) == 2      # the opening run (11 cells: row/column 0 never match) and the ending run
+    kw["threshold"] = 2
+    st, got, _ = H.oracle_run(oracle, season, **kw)
+    assert st == 0 and all(r[:3] == (1, 1, 1) for r in got)
+    # opening: from the timestamp of index 0 (Q3: one before the first matching cell) to index 11 minus the hash duration
+    assert got[0][3] == int(season.ts_ns[0]) and got[0][4] == int(season.ts_ns[11]) - synth.HASH_DURATION_NS
