@@ -1,5 +1,5 @@
 """Quick timings of the other BASELINE configs on one GPU (development aid, not the bench
-contract; bench.py measures configs[1]).  Prints one JSON object.
+contract; bench.py measures configs[3], [4] and [1]).  Prints one JSON object.
 
   config 3: 12 x 60 min, 66 pairs, opening + ending search (hashes resident)
   config 4: search-only, 200 x 24 min, 19,900 pairs (hashes resident; also from host arrays)
