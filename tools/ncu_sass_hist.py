@@ -1,4 +1,5 @@
-"""Dynamic SASS opcode histogram of an `ncu --page source --csv --print-source sass` export:\n    python tools/ncu_sass_hist.py file.csv [units]    (units = frames or words the launch processed)"""
+"""Dynamic SASS opcode histogram of an `ncu --page source --csv --print-source sass` export:
+    python tools/ncu_sass_hist.py file.csv [units]    (units = frames or words the launch processed)"""
 import csv, sys, collections, re
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]; ia = hdr.index("Source"); ie = hdr.index("Instructions Executed"); iw=hdr.index("L1 Wavefronts Shared"); istall=hdr.index("# Samples")
